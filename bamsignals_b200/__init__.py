@@ -3,7 +3,7 @@
 Only what the hot path needs lives here: csrc/ (CUDA kernels, host fetch pipeline, C ABI -> libbamsignals_cuda.so)
 and api.py (the Python mirror of the R functions bamCount / bamProfile / bamCoverage and of CountSignals).
 """
-from .api import (BamsignalsError, CountSignals, GRanges, bamCount, bamCoverage, bamProfile,  # noqa: F401
-                  coverage_core, default_opts, flagMask, lib, pileup_core, timings)
+from .api import (BamsignalsError, CountSignals, GRanges, Stage, bamCount, bamCoverage, bamProfile,  # noqa: F401
+                  core_args, coverage_core, default_opts, flagMask, lib, pileup_core, timings)
 
 __version__ = "0.1.0"

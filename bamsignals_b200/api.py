@@ -213,7 +213,7 @@ class BsgTimings(C.Structure):
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
                 ("ms_decode", C.c_double), ("ms_filter", C.c_double), ("ms_join", C.c_double),
                 ("ms_count", C.c_double), ("ms_inflate_gpu", C.c_double), ("ms_kernels", C.c_double),
-                ("reserved", C.c_double * 8)]
+                ("ms_device", C.c_double), ("reserved", C.c_double * 7)]
 
 
 def lib():
@@ -242,6 +242,14 @@ def lib():
     L.bsg_output_layout.argtypes = [C.c_int64, i32p, C.c_int32, C.c_int32, i64p]
     L.bsg_output_layout.restype = C.c_int64
     L.bsg_device_count.restype = C.c_int
+    L.bsg_stage_open.argtypes = [C.POINTER(C.c_void_p)] + region_args + [C.c_int32, C.POINTER(BsgOpts)]
+    L.bsg_stage_open.restype = C.c_int
+    L.bsg_pileup_staged.argtypes = [C.c_void_p, i32p] + [C.c_int32] * 7 + [i32p, i64p]
+    L.bsg_pileup_staged.restype = C.c_int
+    L.bsg_coverage_staged.argtypes = [C.c_void_p, i32p] + [C.c_int32] * 4 + [i32p, i64p]
+    L.bsg_coverage_staged.restype = C.c_int
+    L.bsg_stage_close.argtypes = [C.c_void_p]
+    L.bsg_stage_close.restype = None
     _lib = L
     return L
 
@@ -305,6 +313,64 @@ def coverage_core(bampath, gr, tlen_filter, mapqual=0, requiredF=0, filteredF=-1
                             None if opts is None else C.byref(opts))
     _check(rc)
     return split_signals(flat, off, False)
+
+
+class Stage:
+    """Resident session (bsg_stage_*): the byte ranges `gr` needs (with halo `ext_hint`) are fetched, inflated and
+    uploaded once; every pileup()/coverage() call then runs the device path only.  want_output=False leaves the
+    result in HBM (kernel-only timing)."""
+
+    def __init__(self, bampath, gr, ext_hint=0, opts: Optional[BsgOpts] = None):
+        self._m = marshal_regions(gr)
+        self._h = C.c_void_p()
+        m = self._m
+        _check(lib().bsg_stage_open(C.byref(self._h), os.fsencode(bampath), m.R, m.levels, m.n_levels,
+                                    _p(m.seq_idx, C.c_int32), _p(m.loc, C.c_int32), _p(m.width, C.c_int32),
+                                    _p(m.strand, C.c_int8), int(ext_hint), None if opts is None else C.byref(opts)))
+
+    def pileup(self, tlen_filter, mapqual=0, binsize=1, shift=0, ss=False, requiredF=0, filteredF=-1, pe_mid=False,
+               want_output=True):
+        off = output_layout(self._m.width, int(binsize), bool(ss))
+        flat = np.empty(int(off[-1]), dtype=np.int32) if want_output else None
+        tl = None if tlen_filter is None else np.asarray(tlen_filter, dtype=np.int32)
+        _check(lib().bsg_pileup_staged(self._h, None if tl is None else _p(tl, C.c_int32), int(mapqual), int(binsize),
+                                       int(shift), int(bool(ss)), int(requiredF), int(filteredF), int(bool(pe_mid)),
+                                       None if flat is None else _p(flat, C.c_int32), _p(off, C.c_int64)))
+        return flat
+
+    def coverage(self, tlen_filter, mapqual=0, requiredF=0, filteredF=-1, tspan=False, want_output=True):
+        off = output_layout(self._m.width, 1, False)
+        flat = np.empty(int(off[-1]), dtype=np.int32) if want_output else None
+        tl = None if tlen_filter is None else np.asarray(tlen_filter, dtype=np.int32)
+        _check(lib().bsg_coverage_staged(self._h, None if tl is None else _p(tl, C.c_int32), int(mapqual),
+                                         int(requiredF), int(filteredF), int(bool(tspan)),
+                                         None if flat is None else _p(flat, C.c_int32), _p(off, C.c_int64)))
+        return flat
+
+    def close(self):
+        if self._h:
+            lib().bsg_stage_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def core_args(fn, **kw):
+    """R-level keyword arguments of bamCount / bamProfile / bamCoverage -> the arguments of the native entry point
+    (R/wrappers.R:112-116, :143-147, :165-169)."""
+    if fn == "bamCoverage":
+        pe = _match_arg(kw.get("paired_end", "ignore"), ("ignore", "extend"))
+        return dict(tlen_filter=_tlen(kw.get("tlenFilter"), pe), mapqual=_trunc(kw.get("mapqual", 0)),
+                    requiredF=flagMask(pe), filteredF=_trunc(kw.get("filteredFlag", -1)), tspan=pe == "extend")
+    pe = _match_arg(kw.get("paired_end", "ignore"), ("ignore", "filter", "midpoint"))
+    return dict(tlen_filter=_tlen(kw.get("tlenFilter"), pe), mapqual=_trunc(kw.get("mapqual", 0)),
+                binsize=-1 if fn == "bamCount" else _trunc(kw.get("binsize", 1)), shift=_trunc(kw.get("shift", 0)),
+                ss=bool(kw.get("ss", False)), requiredF=flagMask(pe), filteredF=_trunc(kw.get("filteredFlag", -1)),
+                pe_mid=pe == "midpoint")
 
 
 # ------------------------------------------------------------------------------------------------------------------

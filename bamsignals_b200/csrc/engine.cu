@@ -1,0 +1,718 @@
+// The fetch -> decode -> filter -> join -> count pipeline and the C ABI of libbamsignals_cuda.so.
+//
+// Host side (this file + plan.cpp + bamio.cpp): BAI query -> fetch segments -> worker pool inflates BGZF blocks into
+// pinned staging slots and walks the block_size chain to emit record offsets -> H2D on a copy stream overlapping the
+// decode kernel of the previous batch on the compute stream.  Device side (kernels.cu): K1..K5.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bamio.h"
+#include "common.h"
+#include "kernels.cuh"
+#include "plan.h"
+#include "pool.h"
+
+namespace bsg {
+namespace {
+
+thread_local std::string g_err;
+thread_local bsg_timings g_tm;
+
+constexpr int kSlots = 4;                       // staging ring depth
+constexpr int64_t kDefaultBatch = 64ll << 20;   // uncompressed bytes per batch
+constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
+constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) BSG_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        BSG_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) BSG_CUDA(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        BSG_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Everything cached per device across calls (released by bsg_shutdown).
+struct DeviceCtx {
+    int dev = 0;
+    bool init = false;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    DevBuf d_raw[kSlots], d_offs[kSlots];
+    PinBuf h_raw[kSlots], h_offs[kSlots];
+    cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
+    DevBuf tab[5], c0, c1, tiles_i32, tiles_i64, out, scalars;
+    DevBuf raw_all, offs_all;                   // resident raw bytes of a staged session
+    PinBuf h_scalars, h_out;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_next = 0;
+
+    void ensure_init(int device) {
+        if (init && dev == device) { BSG_CUDA(cudaSetDevice(dev)); return; }
+        dev = device;
+        BSG_CUDA(cudaSetDevice(dev));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; ++i) {
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+        }
+        h_scalars.ensure(sizeof(DeviceScalars));
+        init = true;
+    }
+    cudaEvent_t timing_event() {
+        if (ev_next == ev_pool.size()) {
+            cudaEvent_t e;
+            BSG_CUDA(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_next++];
+    }
+    void release() {
+        if (!init) return;
+        cudaSetDevice(dev);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < kSlots; ++i) {
+            d_raw[i].release(); d_offs[i].release(); h_raw[i].release(); h_offs[i].release();
+            cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_free[i]);
+        }
+        for (auto& b : tab) b.release();
+        c0.release(); c1.release(); tiles_i32.release(); tiles_i64.release(); out.release(); scalars.release();
+        raw_all.release(); offs_all.release(); h_scalars.release(); h_out.release();
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear(); ev_next = 0;
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp);
+        init = false;
+    }
+};
+
+std::mutex g_mu;                                // one call at a time per process (re-entrancy is not required)
+DeviceCtx g_ctx[16];
+std::unique_ptr<Pool> g_pool;
+
+Pool& get_pool(int want) {
+    int n = want > 0 ? want : int(std::thread::hardware_concurrency());
+    if (n < 1) n = 1;
+    if (!g_pool || g_pool->size() != n) g_pool.reset(new Pool(n));
+    return *g_pool;
+}
+
+struct Span { cudaEvent_t a, b; };
+struct KernelTimes {
+    std::vector<Span> decode, filter, join, count, all;
+    int64_t launches = 0;
+};
+
+double sum_ms(const std::vector<Span>& v) {
+    double t = 0;
+    for (auto& s : v) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); t += ms; }
+    return t;
+}
+
+struct Batch {
+    size_t seg_first = 0, seg_last = 0;         // [first, last)
+    uint64_t bytes = 0;                         // staged bytes (sum of segment usize)
+    int64_t n_records = 0;                      // filled by the walk
+    // runtime state
+    std::vector<uint64_t> seg_base;             // byte offset of each segment in the staging buffer
+    std::vector<uint64_t> seg_off_base;         // first slot of each segment in the (sparse) offsets array
+    std::vector<int64_t> seg_count;
+    std::unique_ptr<std::atomic<int>[]> seg_blocks_left;
+    std::atomic<int> segs_left{0};
+    std::mutex m;
+    std::condition_variable cv;
+    bool ready = false;
+    Error err{0, ""};
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Session: one BAM + one region set on one device.
+// ---------------------------------------------------------------------------------------------------------------
+class Session {
+public:
+    Session(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
+            const int32_t* loc, const int32_t* width, const int8_t* strand, const bsg_opts* opts)
+        : bam_(bampath ? bampath : "") {
+        if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) opts_ = *opts;
+        else { memset(&opts_, 0, sizeof opts_); opts_.verify_crc = 1; }
+        resolve_regions(bam_, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg_);
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+            fail(BSG_ECUDA, "no CUDA device available (libbamsignals_cuda has no CPU fallback)");
+        int dev = opts_.n_devices > 0 ? opts_.devices[0] : 0;
+        if (dev < 0 || dev >= ndev) fail(BSG_EARG, "invalid CUDA device index");
+        ctx_ = &g_ctx[dev];
+        ctx_->ensure_init(dev);
+        ctx_->ev_next = 0;
+        pool_ = &get_pool(opts_.inflate_threads);
+        memset(&tm_, 0, sizeof tm_);
+        tm_.n_devices = 1;
+    }
+
+    // Fetch + upload (+ decode unless keep_raw) everything the regions need with halo `ext`.
+    void stage(int64_t ext, bool keep_raw) {
+        if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
+        const double t0 = now_ms();
+        keep_raw_ = keep_raw;
+        segs_.clear();
+        plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
+        const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : kDefaultBatch;
+        // group segments into batches
+        batches_.clear();
+        uint64_t max_batch = 0, total_bytes = 0, total_c = 0;
+        int64_t rows_cap = 0;
+        for (size_t i = 0; i < segs_.size();) {
+            auto b = std::make_unique<Batch>();
+            b->seg_first = i;
+            uint64_t acc = 0;
+            while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= uint64_t(batch_bytes))) {
+                acc += (segs_[i].usize + 15) & ~15ull;
+                ++i;
+            }
+            b->seg_last = i;
+            b->bytes = acc;
+            if (acc >= (1ull << 32) - 64) fail(BSG_ENOMEM, "a single fetch segment exceeds 4 GiB");
+            max_batch = std::max(max_batch, acc);
+            for (size_t k = b->seg_first; k < b->seg_last; ++k) {
+                rows_cap += int64_t((segs_[k].uend - segs_[k].ubeg) / kMinRecord) + 1;
+                total_bytes += segs_[k].usize; total_c += segs_[k].csize;
+            }
+            batches_.push_back(std::move(b));
+        }
+        rows_cap_ = (rows_cap + 3) & ~int64_t(3);
+        tm_.bytes_compressed = int64_t(total_c);
+        tm_.bytes_inflated = int64_t(total_bytes);
+        tm_.n_batches = int64_t(batches_.size());
+        tm_.ms_plan = now_ms() - t0;
+
+        // device + pinned buffers
+        DeviceCtx& c = *ctx_;
+        const size_t max_offs = size_t(max_batch / kMinRecord) + 1;
+        size_t max_segs = 0;
+        for (auto& b : batches_) max_segs = std::max(max_segs, b->seg_last - b->seg_first);
+        for (int s = 0; s < kSlots && s < int(batches_.size()); ++s) {
+            c.h_raw[s].ensure(max_batch + 64);
+            c.h_offs[s].ensure((max_offs + max_segs + 8) * sizeof(uint32_t));
+            if (!keep_raw) {
+                c.d_raw[s].ensure(max_batch + 64);
+                c.d_offs[s].ensure((max_offs + 8) * sizeof(uint32_t));
+            }
+        }
+        if (keep_raw) {
+            size_t tot = 0;
+            for (auto& b : batches_) tot += (b->bytes + 64 + 255) & ~255ull;
+            c.raw_all.ensure(tot + 64);
+            c.offs_all.ensure((size_t(rows_cap_) + batches_.size() + 8) * sizeof(uint32_t));
+        }
+        ensure_table(rows_cap_);
+        c.scalars.ensure(sizeof(DeviceScalars));
+        BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
+
+        run_pipeline();
+        tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
+    }
+
+    // Staged sessions: decode the resident raw batches again (K1), timed.
+    void decode_resident() {
+        DeviceCtx& c = *ctx_;
+        BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
+        int64_t row0 = 0;
+        for (auto& rb : resident_) {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            launch_decode(c.raw_all.as<uint8_t>() + rb.raw_base, c.offs_all.as<uint32_t>() + rb.offs_base, rb.n, row0,
+                          table(), c.scalars.as<DeviceScalars>(), c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.decode.push_back(sp); kt_.launches += rb.n > 0;
+            row0 += rb.n;
+        }
+    }
+
+    void count(Mode mode, const FilterParams& fp, int32_t binsize, int ss, int32_t* out, const int64_t* out_offsets,
+               int32_t* const* out_ptrs, bool want_output) {
+        DeviceCtx& c = *ctx_;
+        const int64_t R = rg_.R;
+        if (!out_offsets) fail(BSG_EARG, "out_offsets is required");
+        const int64_t total = out_offsets[R];
+        // tiles
+        HostTiles ht;
+        const int tile_ints = kTileInts;
+        make_tiles(rg_, mode, binsize, ss, out_offsets, tile_ints, &ht);
+        const int64_t nt = ht.size();
+        tm_.n_tiles = nt;
+        tm_.out_elems = total;
+        c.tiles_i32.ensure(size_t(nt) * 4 * sizeof(int32_t) + 64);
+        c.tiles_i64.ensure(size_t(nt) * 3 * sizeof(int64_t) + 64);
+        c.out.ensure(size_t(total) * sizeof(int32_t) + 64);
+        int32_t* ti = c.tiles_i32.as<int32_t>();
+        int64_t* tl = c.tiles_i64.as<int64_t>();
+        if (nt) {
+            BSG_CUDA(cudaMemcpyAsync(ti, ht.rid.data(), nt * 4, cudaMemcpyHostToDevice, c.s_comp));
+            BSG_CUDA(cudaMemcpyAsync(ti + nt, ht.loc.data(), nt * 4, cudaMemcpyHostToDevice, c.s_comp));
+            BSG_CUDA(cudaMemcpyAsync(ti + 2 * nt, ht.len.data(), nt * 4, cudaMemcpyHostToDevice, c.s_comp));
+            BSG_CUDA(cudaMemcpyAsync(ti + 3 * nt, ht.strand.data(), nt * 4, cudaMemcpyHostToDevice, c.s_comp));
+            BSG_CUDA(cudaMemcpyAsync(tl, ht.out_off.data(), nt * 8, cudaMemcpyHostToDevice, c.s_comp));
+        }
+        TileTable tt{ti, ti + nt, ti + 2 * nt, ti + 3 * nt, tl, tl + nt, tl + 2 * nt};
+        DeviceScalars* sc = c.scalars.as<DeviceScalars>();
+        ReadTable t = table();
+        int32_t* c0 = c.c0.as<int32_t>();
+        int32_t* c1 = c.c1.as<int32_t>();
+
+        {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            if (mode == MODE_COVERAGE) launch_filter_coverage(t, n_rows_, fp, c0, c1, sc, c.s_comp);
+            else launch_filter_pileup(t, n_rows_, fp, c0, c1, sc, c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.filter.push_back(sp); kt_.launches += n_rows_ > 0;
+        }
+        {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            launch_join(t, n_rows_, tt, nt, sc, c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.join.push_back(sp); kt_.launches += nt > 0;
+        }
+        {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            if (mode == MODE_COUNT) launch_count(tt, nt, c0, c1, ss, c.out.as<int32_t>(), sc, c.s_comp);
+            else if (mode == MODE_PROFILE) launch_profile(tt, nt, c0, c1, ss, binsize, ht.max_tile_ints, c.out.as<int32_t>(), sc, c.s_comp);
+            else launch_coverage(tt, nt, c0, c1, ht.max_tile_ints, c.out.as<int32_t>(), sc, c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.count.push_back(sp); kt_.launches += nt > 0;
+        }
+        BSG_CUDA(cudaGetLastError());
+        BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
+
+        // result: device -> host
+        const double t_d2h = now_ms();
+        if (want_output && total > 0) {
+            if (out) {
+                BSG_CUDA(cudaMemcpyAsync(out, c.out.p, size_t(total) * 4, cudaMemcpyDeviceToHost, c.s_comp));
+                BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+            } else if (out_ptrs) {
+                c.h_out.ensure(size_t(total) * 4);
+                BSG_CUDA(cudaMemcpyAsync(c.h_out.p, c.out.p, size_t(total) * 4, cudaMemcpyDeviceToHost, c.s_comp));
+                BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+                const int32_t* src = c.h_out.as<int32_t>();
+                pool_->parallel_for(R, 4096, [&](int64_t a, int64_t b, int) {
+                    for (int64_t i = a; i < b; ++i) {
+                        const int64_t n = out_offsets[i + 1] - out_offsets[i];
+                        if (n > 0 && out_ptrs[i]) memcpy(out_ptrs[i], src + out_offsets[i], size_t(n) * 4);
+                    }
+                });
+            } else {
+                fail(BSG_EARG, "either out or out_ptrs must be given");
+            }
+        }
+        BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        tm_.ms_d2h = now_ms() - t_d2h;
+        const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
+        if (hs->status & STATUS_CORRUPT) fail(BSG_EFORMAT, "corrupt BAM record (CIGAR beyond record end) in " + bam_.path());
+        if (hs->status & STATUS_UNSORTED) fail(BSG_EUNSORTED, "BAM file is not coordinate-sorted: " + bam_.path());
+        tm_.records = n_rows_;
+        tm_.records_kept = int64_t(hs->kept);
+        tm_.candidates = int64_t(hs->candidates);
+    }
+
+    void finish_timings(double t_start) {
+        tm_.ms_decode = sum_ms(kt_.decode);
+        tm_.ms_filter = sum_ms(kt_.filter);
+        tm_.ms_join = sum_ms(kt_.join);
+        tm_.ms_count = sum_ms(kt_.count);
+        tm_.ms_kernels = tm_.ms_decode + tm_.ms_filter + tm_.ms_join + tm_.ms_count;
+        if (!kt_.count.empty()) {
+            const cudaEvent_t first = kt_.decode.empty() ? kt_.filter.front().a : kt_.decode.front().a;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, first, kt_.count.back().b);
+            tm_.ms_device = ms;
+        }
+        tm_.n_launches = kt_.launches;
+        tm_.ms_total = now_ms() - t_start;
+        g_tm = tm_;
+        kt_ = KernelTimes();
+        ctx_->ev_next = 0;
+    }
+    void reset_counters() { int nd = tm_.n_devices; int64_t bc = tm_.bytes_compressed, bi = tm_.bytes_inflated, nb = tm_.n_batches;
+        memset(&tm_, 0, sizeof tm_); tm_.n_devices = nd; tm_.bytes_compressed = bc; tm_.bytes_inflated = bi; tm_.n_batches = nb; }
+
+    int64_t n_rows() const { return n_rows_; }
+
+private:
+    ReadTable table() {
+        DeviceCtx& c = *ctx_;
+        return ReadTable{c.tab[0].as<int32_t>(), c.tab[1].as<int32_t>(), c.tab[2].as<int32_t>(), c.tab[3].as<int32_t>(), c.tab[4].as<uint32_t>()};
+    }
+    void ensure_table(int64_t rows) {
+        DeviceCtx& c = *ctx_;
+        const size_t bytes = size_t(rows + 4) * 4;
+        for (auto& b : c.tab) b.ensure(bytes);
+        c.c0.ensure(bytes); c.c1.ensure(bytes);
+    }
+
+    // Inflate + walk one batch on the pool; the last worker to finish marks it ready.
+    void submit_batch(Batch* b, int slot) {
+        DeviceCtx& c = *ctx_;
+        uint8_t* stage = c.h_raw[slot].as<uint8_t>();
+        uint32_t* offs = c.h_offs[slot].as<uint32_t>();
+        const size_t ns = b->seg_last - b->seg_first;
+        b->seg_base.resize(ns); b->seg_off_base.resize(ns); b->seg_count.assign(ns, 0);
+        b->seg_blocks_left.reset(new std::atomic<int>[ns]);
+        uint64_t base = 0, obase = 0;
+        for (size_t k = 0; k < ns; ++k) {
+            const Segment& s = segs_[b->seg_first + k];
+            b->seg_base[k] = base; b->seg_off_base[k] = obase;
+            base += (s.usize + 15) & ~15ull;
+            obase += (s.uend - s.ubeg) / kMinRecord + 1;
+            b->seg_blocks_left[k].store(int(s.blocks.size()));
+        }
+        b->segs_left.store(int(ns));
+        b->ready = false;
+        const bool crc = opts_.verify_crc != 0;
+        auto seg_done = [this, b, stage, offs](size_t k) {
+            // walk the block_size chain of segment k
+            const Segment& s = segs_[b->seg_first + k];
+            try {
+                const uint64_t sb = b->seg_base[k];
+                uint64_t p = sb + s.ubeg;
+                const uint64_t e = sb + s.uend;
+                uint32_t* o = offs + b->seg_off_base[k];
+                int64_t n = 0;
+                while (p < e) {
+                    if (p + 4 > e) fail(BSG_EFORMAT, "truncated BAM record in " + bam_.path());
+                    const int32_t bs = rd_i32(stage + p);
+                    if (bs < 32 || p + 4 + uint64_t(bs) > e) fail(BSG_EFORMAT, "corrupt BAM record chain in " + bam_.path());
+                    o[n++] = uint32_t(p);
+                    p += 4 + uint64_t(bs);
+                }
+                b->seg_count[k] = n;
+            } catch (Error& er) {
+                std::lock_guard<std::mutex> g(b->m);
+                if (!b->err.code) b->err = er;
+            }
+            if (b->segs_left.fetch_sub(1) == 1) {
+                // finalize: compact the per-segment offset runs, append the end sentinel
+                const size_t ns2 = b->seg_last - b->seg_first;
+                int64_t n = 0;
+                for (size_t q = 0; q < ns2; ++q) {
+                    if (b->seg_off_base[q] != uint64_t(n) && b->seg_count[q])
+                        memmove(offs + n, offs + b->seg_off_base[q], size_t(b->seg_count[q]) * 4);
+                    n += b->seg_count[q];
+                }
+                const Segment& last = segs_[b->seg_last - 1];
+                offs[n] = uint32_t(b->seg_base[ns2 - 1] + last.uend);
+                b->n_records = n;
+                std::lock_guard<std::mutex> g(b->m);
+                b->ready = true;
+                b->cv.notify_all();
+            }
+        };
+        for (size_t k = 0; k < ns; ++k) {
+            const Segment& s = segs_[b->seg_first + k];
+            if (s.blocks.empty()) { pool_->submit([seg_done, k](int) { seg_done(k); }); continue; }
+            const size_t group = 8;
+            uint64_t ub = 0;
+            for (size_t g0 = 0; g0 < s.blocks.size(); g0 += group) {
+                const size_t g1 = std::min(s.blocks.size(), g0 + group);
+                const uint64_t ub0 = ub;
+                for (size_t q = g0; q < g1; ++q) ub += s.blocks[q].isize;
+                pool_->submit([this, b, &s, k, g0, g1, ub0, stage, crc, seg_done](int) {
+                    try {
+                        thread_local Inflater inf;
+                        uint64_t u = b->seg_base[k] + ub0;
+                        for (size_t q = g0; q < g1; ++q) {
+                            inf.inflate_block(bam_.data(), s.blocks[q], stage + u, crc);
+                            u += s.blocks[q].isize;
+                        }
+                    } catch (Error& er) {
+                        std::lock_guard<std::mutex> g(b->m);
+                        if (!b->err.code) b->err = er;
+                    }
+                    if (b->seg_blocks_left[k].fetch_sub(int(g1 - g0)) == int(g1 - g0)) seg_done(k);
+                });
+            }
+        }
+    }
+
+    void run_pipeline() {
+        DeviceCtx& c = *ctx_;
+        const size_t nb = batches_.size();
+        resident_.clear();
+        n_rows_ = 0;
+        size_t next_submit = 0;
+        uint64_t raw_base = 0; int64_t offs_base = 0;
+        double h2d_ms = 0;
+        try {
+        for (size_t commit = 0; commit < nb; ++commit) {
+            while (next_submit < nb && next_submit < commit + kSlots) {
+                const int slot = int(next_submit % kSlots);
+                if (next_submit >= size_t(kSlots)) BSG_CUDA(cudaEventSynchronize(c.ev_free[slot]));
+                submit_batch(batches_[next_submit].get(), slot);
+                ++next_submit;
+            }
+            Batch* b = batches_[commit].get();
+            {
+                std::unique_lock<std::mutex> lk(b->m);
+                b->cv.wait(lk, [&] { return b->ready; });
+            }
+            if (b->err.code) throw b->err;
+            const int slot = int(commit % kSlots);
+            const int64_t n = b->n_records;
+            if (n_rows_ + n > rows_cap_) fail(BSG_EFORMAT, "record count exceeds the planned table capacity");
+            const double t0 = now_ms();
+            uint8_t* d_raw; uint32_t* d_offs;
+            if (keep_raw_) {
+                d_raw = c.raw_all.as<uint8_t>() + raw_base;
+                d_offs = c.offs_all.as<uint32_t>() + offs_base;
+                resident_.push_back(ResidentBatch{raw_base, offs_base, n});
+                raw_base += (b->bytes + 64 + 255) & ~255ull;
+                offs_base += n + 1;
+            } else {
+                d_raw = c.d_raw[slot].as<uint8_t>();
+                d_offs = c.d_offs[slot].as<uint32_t>();
+            }
+            BSG_CUDA(cudaMemcpyAsync(d_raw, c.h_raw[slot].p, b->bytes + 16, cudaMemcpyHostToDevice, c.s_copy));
+            BSG_CUDA(cudaMemcpyAsync(d_offs, c.h_offs[slot].p, size_t(n + 1) * 4, cudaMemcpyHostToDevice, c.s_copy));
+            BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
+            if (keep_raw_) {
+                BSG_CUDA(cudaEventRecord(c.ev_free[slot], c.s_copy));
+            } else {
+                BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
+                Span sp{c.timing_event(), c.timing_event()};
+                BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+                launch_decode(d_raw, d_offs, n, n_rows_, table(), c.scalars.as<DeviceScalars>(), c.s_comp);
+                BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+                BSG_CUDA(cudaEventRecord(c.ev_free[slot], c.s_comp));
+                kt_.decode.push_back(sp); kt_.launches += n > 0;
+            }
+            h2d_ms += now_ms() - t0;
+            n_rows_ += n;
+        }
+        } catch (...) {
+            // workers still reference this Session and the staging slots: wait for every submitted batch
+            for (size_t k = 0; k < next_submit; ++k) {
+                std::unique_lock<std::mutex> lk(batches_[k]->m);
+                batches_[k]->cv.wait(lk, [&] { return batches_[k]->ready; });
+            }
+            cudaStreamSynchronize(c.s_copy); cudaStreamSynchronize(c.s_comp);
+            throw;
+        }
+        BSG_CUDA(cudaStreamSynchronize(c.s_copy));
+        if (keep_raw_) BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        tm_.ms_h2d = h2d_ms;
+        tm_.records = n_rows_;
+    }
+
+    struct ResidentBatch { uint64_t raw_base; int64_t offs_base; int64_t n; };
+
+    BamFile bam_;
+    bsg_opts opts_;
+    Regions rg_;
+    DeviceCtx* ctx_ = nullptr;
+    Pool* pool_ = nullptr;
+    std::vector<Segment> segs_;
+    std::vector<std::unique_ptr<Batch>> batches_;
+    std::vector<ResidentBatch> resident_;
+    int64_t rows_cap_ = 0, n_rows_ = 0;
+    bool keep_raw_ = false;
+    KernelTimes kt_;
+    bsg_timings tm_;
+};
+
+FilterParams make_params(const int32_t* tlen_filter, int32_t mapqual, int32_t shift, int32_t requiredF, int32_t filteredF,
+                         int32_t pe_mid, int32_t tspan) {
+    FilterParams p;
+    memset(&p, 0, sizeof p);
+    p.mapqual = mapqual;
+    p.required = uint32_t(requiredF);
+    p.filtered = uint32_t(filteredF);
+    p.have_tlen = tlen_filter != nullptr;
+    if (tlen_filter) { p.tmin = tlen_filter[0]; p.tmax = tlen_filter[1]; }
+    p.midpoint = pe_mid != 0;
+    p.shift = shift;
+    p.tspan = tspan != 0;
+    return p;
+}
+
+int64_t ext_pileup(const int32_t* tlen_filter, int32_t shift, int32_t pe_mid) {
+    if (pe_mid && !tlen_filter) fail(BSG_EARG, "pe_mid requires a tlen_filter");      // the reference would read tlen_filter[1]
+    return std::abs(int64_t(shift)) + (pe_mid ? int64_t(tlen_filter[1]) : 0);         // src/bamsignals.cpp:457
+}
+int64_t ext_coverage(const int32_t* tlen_filter, int32_t tspan) {
+    if (tspan && !tlen_filter) fail(BSG_EARG, "tspan requires a tlen_filter");
+    return tspan ? int64_t(tlen_filter[1]) : 0;                                       // src/bamsignals.cpp:487
+}
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        std::lock_guard<std::mutex> g(g_mu);
+        f();
+        return BSG_OK;
+    } catch (Error& e) {
+        g_err = e.msg;
+        cudaGetLastError();
+        return e.code;
+    } catch (std::bad_alloc&) {
+        g_err = "out of host memory";
+        return BSG_ENOMEM;
+    } catch (std::exception& e) {
+        g_err = std::string("internal error: ") + e.what();
+        return BSG_EARG;
+    }
+}
+
+}  // namespace
+}  // namespace bsg
+
+using namespace bsg;
+
+struct bsg_stage {
+    std::unique_ptr<Session> s;
+};
+
+extern "C" {
+
+int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
+               const int32_t* loc, const int32_t* width, const int8_t* strand, const int32_t* tlen_filter,
+               int32_t mapqual, int32_t binsize, int32_t shift, int32_t ss, int32_t requiredF, int32_t filteredF,
+               int32_t pe_mid, int32_t /*maxgap*/, int32_t* out, const int64_t* out_offsets, int32_t* const* out_ptrs,
+               const bsg_opts* opts) {
+    return guarded([&] {
+        const double t0 = now_ms();
+        Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
+        const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
+        s.stage(ext, false);
+        const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
+        s.count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, out, out_offsets, out_ptrs, true);
+        s.finish_timings(t0);
+    });
+}
+
+int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
+                 const int32_t* loc, const int32_t* width, const int8_t* strand, const int32_t* tlen_filter,
+                 int32_t mapqual, int32_t requiredF, int32_t filteredF, int32_t tspan, int32_t /*maxgap*/, int32_t* out,
+                 const int64_t* out_offsets, int32_t* const* out_ptrs, const bsg_opts* opts) {
+    return guarded([&] {
+        const double t0 = now_ms();
+        Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
+        s.stage(ext_coverage(tlen_filter, tspan), false);
+        const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
+        s.count(MODE_COVERAGE, fp, 1, 0, out, out_offsets, out_ptrs, true);
+        s.finish_timings(t0);
+    });
+}
+
+int64_t bsg_output_layout(int64_t R, const int32_t* width, int32_t binsize, int32_t ss, int64_t* offsets) {
+    const int64_t mult = ss ? 2 : 1;
+    int64_t acc = 0;
+    for (int64_t i = 0; i < R; ++i) {
+        offsets[i] = acc;
+        acc += binsize <= 0 ? mult : mult * ((int64_t(width[i]) + binsize - 1) / binsize);
+    }
+    offsets[R] = acc;
+    return acc;
+}
+
+int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                   const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                   int32_t ext_hint, const bsg_opts* opts) {
+    if (!st) { g_err = "null stage pointer"; return BSG_EARG; }
+    *st = nullptr;
+    return guarded([&] {
+        const double t0 = now_ms();
+        auto h = std::make_unique<bsg_stage>();
+        h->s.reset(new Session(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts));
+        h->s->stage(ext_hint, true);
+        h->s->finish_timings(t0);
+        *st = h.release();
+    });
+}
+
+int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t binsize, int32_t shift,
+                      int32_t ss, int32_t requiredF, int32_t filteredF, int32_t pe_mid, int32_t* out,
+                      const int64_t* out_offsets) {
+    if (!st || !st->s) { g_err = "null stage"; return BSG_EARG; }
+    return guarded([&] {
+        const double t0 = now_ms();
+        st->s->reset_counters();
+        (void)ext_pileup(tlen_filter, shift, pe_mid);
+        st->s->decode_resident();
+        const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
+        st->s->count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, out, out_offsets, nullptr, out != nullptr);
+        st->s->finish_timings(t0);
+    });
+}
+
+int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t requiredF,
+                        int32_t filteredF, int32_t tspan, int32_t* out, const int64_t* out_offsets) {
+    if (!st || !st->s) { g_err = "null stage"; return BSG_EARG; }
+    return guarded([&] {
+        const double t0 = now_ms();
+        st->s->reset_counters();
+        (void)ext_coverage(tlen_filter, tspan);
+        st->s->decode_resident();
+        const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
+        st->s->count(MODE_COVERAGE, fp, 1, 0, out, out_offsets, nullptr, out != nullptr);
+        st->s->finish_timings(t0);
+    });
+}
+
+void bsg_stage_close(bsg_stage* st) {
+    if (!st) return;
+    std::lock_guard<std::mutex> g(g_mu);
+    delete st;
+}
+
+const char* bsg_last_error(void) { return g_err.c_str(); }
+
+int bsg_get_timings(bsg_timings* t) {
+    if (!t) return BSG_EARG;
+    *t = g_tm;
+    return BSG_OK;
+}
+
+int bsg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void bsg_shutdown(void) {
+    std::lock_guard<std::mutex> g(g_mu);
+    for (auto& c : g_ctx) c.release();
+    g_pool.reset();
+}
+
+const char* bsg_version(void) { return "bamsignals_cuda 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// Hand-written sm_100a kernels of the counting path.  Integer / byte work bounded by HBM bandwidth and shared-memory
+// atomics: no tensor cores by design (nothing here is a dense contraction).  See kernels.cuh for the data layout and
+// DESIGN.md for the per-kernel algorithmic bytes.
+#include "kernels.cuh"
+
+#include <climits>
+
+namespace bsg {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 decode.  One thread per record.  Records start at arbitrary byte offsets, so every field is assembled from
+// aligned 32-bit words with a funnel shift; neighbouring threads read neighbouring records, so the words come from
+// the same few 128-byte lines (L1 absorbs the overlap, DRAM sees each byte once).
+// Fixed part of a record (offsets from the block_size field): refID +4, pos +8, l_read_name +12, mapq +13,
+// bin +14, n_cigar_op +16, flag +18, l_seq +20, next_refID +24, next_pos +28, tlen +32, read_name +36, cigar after.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_decode(const uint8_t* __restrict__ raw, const uint32_t* __restrict__ offs,
+                                                     int n, int64_t row0, ReadTable t, DeviceScalars* sc) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const bool active = i < n;
+    int32_t tid = -1, pos = -1;
+    uint32_t bad = 0;
+    if (active) {
+        const uint32_t o = offs[i];
+        const uint32_t rec_end = offs[i + 1];
+        const uint32_t a = o + 4;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (a & ~3u));
+        const uint32_t sh = (a & 3u) * 8;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+        const uint32_t w7 = __ldg(w + 7), w8 = __ldg(w + 8);
+        tid = int32_t(__funnelshift_r(w0, w1, sh));
+        pos = int32_t(__funnelshift_r(w1, w2, sh));
+        const uint32_t nm = __funnelshift_r(w2, w3, sh);   // l_read_name | mapq << 8 | bin << 16
+        const uint32_t cf = __funnelshift_r(w3, w4, sh);   // n_cigar_op | flag << 16
+        const int32_t tlen = int32_t(__funnelshift_r(w7, w8, sh));
+        const uint32_t l_name = nm & 0xffu, mapq = (nm >> 8) & 0xffu;
+        const uint32_t n_cigar = cf & 0xffffu, flag = cf >> 16;
+        const uint32_t c = o + 36 + l_name;
+        uint32_t rlen = 0;
+        if (c + 4u * n_cigar > rec_end) {
+            bad = STATUS_CORRUPT;
+        } else if (!(flag & 0x4u) && n_cigar) {             // bam_endpos: unmapped reads have no reference length
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(raw + (c & ~3u));
+            const uint32_t csh = (c & 3u) * 8;
+            uint32_t lo = __ldg(cw);
+            for (uint32_t k = 0; k < n_cigar; ++k) {
+                const uint32_t hi = __ldg(cw + k + 1);
+                const uint32_t op = __funnelshift_r(lo, hi, csh);
+                lo = hi;
+                if ((0x18Du >> (op & 0xfu)) & 1u) rlen += op >> 4;   // M, D, N, =, X consume the reference
+            }
+        }
+        if (rlen == 0) rlen = 1;
+        const int64_t row = row0 + i;
+        t.tid[row] = tid;
+        t.pos[row] = pos;
+        t.end[row] = int32_t(uint32_t(pos) + rlen - 1u);
+        t.tlen[row] = tlen;
+        t.flagmq[row] = flag | (mapq << 16);
+    }
+    // coordinate-sortedness: compare with the previous record (previous lane; lane 0 re-reads it)
+    const int lane = threadIdx.x & 31;
+    uint32_t ptid = __shfl_up_sync(FULL, uint32_t(tid), 1);
+    int32_t ppos = __shfl_up_sync(FULL, pos, 1);
+    bool have_prev = active;
+    if (lane == 0 && active) {
+        if (i > 0) {
+            const uint32_t a = offs[i - 1] + 4;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (a & ~3u));
+            const uint32_t sh = (a & 3u) * 8;
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+            ptid = __funnelshift_r(w0, w1, sh);
+            ppos = int32_t(__funnelshift_r(w1, w2, sh));
+        } else if (row0 > 0) {
+            ptid = uint32_t(t.tid[row0 - 1]);
+            ppos = t.pos[row0 - 1];
+        } else {
+            have_prev = false;
+        }
+    }
+    if (have_prev && (uint32_t(tid) < ptid || (uint32_t(tid) == ptid && pos < ppos))) bad |= STATUS_UNSORTED;
+    if (bad) atomicOr(&sc->status, bad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2 filter + coordinate.  Four reads per thread with 128-bit loads and stores.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool keep_read(const FilterParams& p, uint32_t fm, int32_t tlen, int32_t* abs_tlen) {
+    const uint32_t flag = fm & 0xffffu, mapq = fm >> 16;
+    const int32_t a = tlen < 0 ? -tlen : tlen;   // abs() as the reference computes it (INT_MIN stays negative)
+    *abs_tlen = a;
+    bool keep = int32_t(mapq) >= p.mapqual;
+    keep = keep && !(p.required & ~flag);          // every required bit present   (src/bamsignals.cpp:21-23, :328)
+    keep = keep && (p.filtered & ~flag);           // not all filtered bits present (:329); filtered == 0 drops all
+    keep = keep && (!p.have_tlen || (a >= p.tmin && a <= p.tmax));
+    return keep;
+}
+
+template <bool COVERAGE>
+__global__ void __launch_bounds__(kThreads) k_filter(const int4* __restrict__ pos4, const int4* __restrict__ end4,
+                                                     const int4* __restrict__ tlen4, const uint4* __restrict__ fm4,
+                                                     int64_t n, FilterParams p, int4* __restrict__ c0v,
+                                                     int4* __restrict__ c1v, DeviceScalars* sc) {
+    const int64_t q = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t n4 = (n + 3) >> 2;
+    int hlo = INT_MIN, hhi = INT_MIN, kept = 0;
+    if (q < n4) {
+        const int4 P = __ldg(pos4 + q), E = __ldg(end4 + q), T = __ldg(tlen4 + q);
+        const uint4 F = __ldg(fm4 + q);
+        const int32_t ps[4] = {P.x, P.y, P.z, P.w}, es[4] = {E.x, E.y, E.z, E.w}, ts[4] = {T.x, T.y, T.z, T.w};
+        const uint32_t fs[4] = {F.x, F.y, F.z, F.w};
+        int32_t o0[4], o1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int32_t a;
+            const bool keep = (4 * q + j < n) && keep_read(p, fs[j], ts[j], &a);
+            const bool neg = (fs[j] & 0x10u) != 0;
+            if (!COVERAGE) {
+                const int32_t offset = p.midpoint ? a / 2 + p.shift : p.shift;               // :339
+                const int32_t pos5 = neg ? es[j] - offset : ps[j] + offset;                  // :340-344
+                o0[j] = pos5;
+                o1[j] = keep ? int32_t(neg) : -1;
+                if (keep) { hlo = max(hlo, pos5 - ps[j]); hhi = max(hhi, ps[j] - pos5); }
+            } else {
+                int32_t s = ps[j], e = es[j];                                                 // :401-403
+                if (p.tspan) {
+                    if (neg && ts[j] < 0) s = e + ts[j] + 1;                                  // :408-409
+                    else if (!neg && ts[j] > 0) e = s + ts[j] - 1;                            // :410-411
+                }
+                o0[j] = keep ? s : INT_MAX;
+                o1[j] = keep ? e : INT_MIN;
+                if (keep) { hlo = max(hlo, e - ps[j]); hhi = max(hhi, ps[j] - s); }
+            }
+            kept += keep;
+        }
+        c0v[q] = make_int4(o0[0], o0[1], o0[2], o0[3]);
+        c1v[q] = make_int4(o1[0], o1[1], o1[2], o1[3]);
+    }
+    __shared__ int s_lo[kThreads / 32], s_hi[kThreads / 32], s_k[kThreads / 32];
+    hlo = warp_max(hlo); hhi = warp_max(hhi); kept = warp_sum(kept);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_lo[wid] = hlo; s_hi[wid] = hhi; s_k[wid] = kept; }
+    __syncthreads();
+    if (wid == 0) {
+        hlo = lane < kThreads / 32 ? s_lo[lane] : INT_MIN;
+        hhi = lane < kThreads / 32 ? s_hi[lane] : INT_MIN;
+        kept = lane < kThreads / 32 ? s_k[lane] : 0;
+        hlo = warp_max(hlo); hhi = warp_max(hhi); kept = warp_sum(kept);
+        if (lane == 0) {
+            if (hlo > sc->halo_lo) atomicMax(&sc->halo_lo, hlo);
+            if (hhi > sc->halo_hi) atomicMax(&sc->halo_hi, hhi);
+            if (kept) atomicAdd(&sc->kept, (unsigned long long)kept);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3 region join: two binary searches per tile over the (tid,pos)-sorted table.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t lower_bound_tp(const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                                  int64_t n, uint32_t ktid, int64_t kpos) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint32_t t = uint32_t(__ldg(tid + mid));
+        const int64_t p = __ldg(pos + mid);
+        const bool less = t < ktid || (t == ktid && p < kpos);
+        if (less) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kThreads) k_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles,
+                                                   const DeviceScalars* sc_in, DeviceScalars* sc) {
+    const int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+    long long cand = 0;
+    if (i < n_tiles) {
+        const int64_t halo_lo = sc_in->halo_lo, halo_hi = sc_in->halo_hi;
+        const uint32_t rid = uint32_t(tiles.rid[i]);
+        const int64_t loc = tiles.loc[i], len = tiles.len[i];
+        const int64_t lo = lower_bound_tp(t.tid, t.pos, n, rid, loc - halo_lo);
+        const int64_t hi = lower_bound_tp(t.tid, t.pos, n, rid, loc + len + halo_hi);
+        tiles.cand_lo[i] = lo;
+        tiles.cand_hi[i] = hi > lo ? hi : lo;
+        cand = hi > lo ? hi - lo : 0;
+    }
+    // block reduce the candidate count (diagnostic: C in the 8*C + 4*B algorithmic-byte formula)
+    __shared__ long long s_c[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(FULL, cand, o);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = cand;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int k = 0; k < kThreads / 32; ++k) tot += s_c[k];
+        if (tot) atomicAdd(&sc->candidates, (unsigned long long)tot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4 bamCount: one warp per region, per-lane counters, no atomics.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_count(TileTable tiles, int64_t n_tiles, const int32_t* __restrict__ c0,
+                                                    const int32_t* __restrict__ c1, int ss, int32_t* __restrict__ out) {
+    const int64_t w = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (w >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t lo = tiles.cand_lo[w], hi = tiles.cand_hi[w];
+    const int32_t loc = tiles.loc[w];
+    const uint32_t len = uint32_t(tiles.len[w]);
+    const int flip = tiles.strand[w] < 0 ? 1 : 0;
+    int sense = 0, anti = 0;
+    for (int64_t i = lo + lane; i < hi; i += 32) {
+        const int32_t p5 = __ldg(c0 + i), ng = __ldg(c1 + i);
+        const bool ok = ng >= 0 && uint32_t(p5 - loc) < len;                 // src/bamsignals.cpp:351-353
+        const int a = (ng ^ flip) & 1;                                        // :355-359
+        sense += ok && !a;
+        anti += ok && a;
+    }
+    sense = warp_sum(sense);
+    anti = warp_sum(anti);
+    if (lane == 0) {
+        const int64_t off = tiles.out_off[w];
+        if (ss) { out[off] = sense; out[off + 1] = anti; } else { out[off] = sense + anti; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared -> global write-out of one tile.  `sm` was placed so that sm and dst have the same phase modulo four
+// ints, which lets the body move as 128-bit shared loads + 128-bit streaming stores.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_out(int32_t* __restrict__ dst, const int32_t* sm, int n) {
+    const int head = min(n, int((4 - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3));
+    if (int(threadIdx.x) < head) __stcs(dst + threadIdx.x, sm[threadIdx.x]);
+    const int body = (n - head) >> 2;
+    int4* d4 = reinterpret_cast<int4*>(dst + head);
+    const int4* s4 = reinterpret_cast<const int4*>(sm + head);
+    for (int k = threadIdx.x; k < body; k += blockDim.x) __stcs(d4 + k, s4[k]);
+    for (int k = head + 4 * body + threadIdx.x; k < n; k += blockDim.x) __stcs(dst + k, sm[k]);
+}
+
+// exact floor(n / d) for 0 <= n < 2^31 with a precomputed multiplier (host: magic_for())
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic, uint32_t shift) {
+    return uint32_t((uint64_t(n) * magic) >> shift);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4 bamProfile: one CTA per tile (<= kTileInts output ints), shared-memory histogram.
+// AGG: the table is coordinate-sorted, so for binsize >> 1 consecutive lanes mostly fall into the same bin; runs
+// of equal bins inside a warp are detected with one shuffle + one ballot and collapsed to one shared atomic per
+// run (and per strand when ss), instead of one atomic per read.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool SS, bool BIN1, bool AGG>
+__global__ void __launch_bounds__(kThreads) k_profile(TileTable tiles, const int32_t* __restrict__ c0,
+                                                      const int32_t* __restrict__ c1, int32_t binsize, uint64_t magic,
+                                                      uint32_t mshift, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) int32_t smem[];
+    const int64_t tix = blockIdx.x;
+    const int32_t loc = tiles.loc[tix], len = tiles.len[tix];
+    const int flip = tiles.strand[tix] < 0 ? 1 : 0;
+    const int64_t lo = tiles.cand_lo[tix], hi = tiles.cand_hi[tix];
+    const int64_t off = tiles.out_off[tix];
+    const int nbins = BIN1 ? len : int((uint32_t(len) + uint32_t(binsize) - 1u) / uint32_t(binsize));
+    const int nout = SS ? 2 * nbins : nbins;
+    int32_t* hist = smem + (off & 3);                      // same 16-byte phase as the destination
+    for (int k = threadIdx.x; k < nout; k += kThreads) hist[k] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = lo + (threadIdx.x & ~31); base < hi; base += kThreads) {   // whole warps iterate together
+        const int64_t i = base + lane;
+        bool ok = false;
+        int32_t bin = -1, a = 0;
+        if (i < hi) {
+            const int32_t p5 = __ldg(c0 + i), ng = __ldg(c1 + i);
+            int32_t rel = p5 - loc;
+            ok = ng >= 0 && uint32_t(rel) < uint32_t(len);                         // src/bamsignals.cpp:351-353
+            a = (ng ^ flip) & 1;
+            if (flip) rel = len - 1 - rel;                                         // :356-359
+            if (ok) bin = BIN1 ? rel : int32_t(fast_div(uint32_t(rel), magic, mshift));
+        }
+        if (!AGG) {
+            if (ok) atomicAdd(&hist[SS ? 2 * bin + a : bin], 1);                   // :361-362
+        } else {
+            const int32_t prev = __shfl_up_sync(FULL, bin, 1);
+            const bool head = lane == 0 || bin != prev;
+            const uint32_t heads = __ballot_sync(FULL, head);
+            const uint32_t antis = __ballot_sync(FULL, a != 0);
+            if (ok && head) {
+                const uint32_t after = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+                const int next = after ? __ffs(after) - 1 : 32;
+                const uint32_t below_next = next == 32 ? FULL : ((1u << next) - 1u);
+                const uint32_t run = below_next & ~((1u << lane) - 1u);
+                if (SS) {
+                    const int ns = __popc(run & ~antis), na = __popc(run & antis);
+                    if (ns) atomicAdd(&hist[2 * bin], ns);
+                    if (na) atomicAdd(&hist[2 * bin + 1], na);
+                } else {
+                    atomicAdd(&hist[bin], __popc(run));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    copy_out(out + off, hist, nout);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5 bamCoverage: one CTA per tile; +1/-1 into a shared difference array, then a block-wide inclusive scan
+// (4 ints per thread, warp shuffles, one carry per 1024-element chunk) done in place, then the coalesced write-out.
+// A tile is treated as its own region: the clamp max(start - loc, 0) makes every tile's scan self-contained.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const int32_t* __restrict__ c0,
+                                                       const int32_t* __restrict__ c1, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) int32_t smem[];
+    __shared__ int32_t s_warp[kThreads / 32];
+    __shared__ int32_t s_carry;
+    const int64_t tix = blockIdx.x;
+    const int32_t loc = tiles.loc[tix], len = tiles.len[tix];
+    const bool neg_region = tiles.strand[tix] < 0;
+    const int64_t lo = tiles.cand_lo[tix], hi = tiles.cand_hi[tix];
+    const int64_t off = tiles.out_off[tix];
+    const int32_t rend = loc + len;                          // region end, exclusive
+    // d[j] <-> out[off + j]; d sits `ph` ints into the 16-byte aligned buffer so that shared and global addresses
+    // have the same phase; the ph leading ints are zeros and simply take part in the scan.
+    const int ph = int(off & 3);
+    int32_t* d = smem + ph;
+    const int total = ph + len;
+    const int padded = (total + 3) & ~3;
+    for (int k = threadIdx.x; k < padded; k += kThreads) smem[k] = 0;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const int32_t s = __ldg(c0 + i), e = __ldg(c1 + i);
+        if (s >= rend || e < loc) continue;                  // src/bamsignals.cpp:420 (dropped reads: s = INT_MAX)
+        int32_t up, down;
+        if (!neg_region) { up = s - loc; down = e + 1 - loc; }          // :423-428
+        else { up = rend - 1 - e; down = rend - s; }                    // :431-436
+        atomicAdd(&d[up > 0 ? up : 0], 1);
+        if (down < len) atomicAdd(&d[down], -1);
+    }
+    __syncthreads();
+    // in-place inclusive scan of smem[0, total)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* base = smem;
+    for (int c0i = 0; c0i < total; c0i += kThreads * 4) {
+        const int idx = c0i + threadIdx.x * 4;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (idx < total) v = *reinterpret_cast<const int4*>(base + idx);   // tail ints beyond len are zero
+        v.y += v.x; v.z += v.y; v.w += v.z;
+        int incl = v.w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        int prefix = s_carry + incl - v.w;
+        for (int k = 0; k < wid; ++k) prefix += s_warp[k];
+        const int through = prefix + v.w;                    // inclusive sum through this thread's four ints
+        if (idx < total) {
+            v.x += prefix; v.y += prefix; v.z += prefix; v.w += prefix;
+            *reinterpret_cast<int4*>(base + idx) = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) s_carry = through;
+        __syncthreads();
+    }
+    copy_out(out + off, d, len);
+}
+
+void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
+    uint32_t L = 0;
+    while ((1ull << L) < uint64_t(d)) ++L;
+    *shift = 32 + L;
+    const unsigned __int128 num = (unsigned __int128)1 << (32 + L);
+    *magic = uint64_t((num + uint64_t(d) - 1) / uint64_t(d));
+}
+
+}  // namespace
+
+void launch_decode(const uint8_t* raw, const uint32_t* offs, int64_t n, int64_t row0, ReadTable t, DeviceScalars* sc,
+                   cudaStream_t s) {
+    if (n <= 0) return;
+    const int64_t grid = (n + kThreads - 1) / kThreads;
+    k_decode<<<unsigned(grid), kThreads, 0, s>>>(raw, offs, int(n), row0, t, sc);
+}
+
+void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
+    if (n <= 0) return;
+    const int64_t n4 = (n + 3) / 4, grid = (n4 + kThreads - 1) / kThreads;
+    k_filter<false><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
+                                                        (const uint4*)t.flagmq, n, p, (int4*)c0, (int4*)c1, sc);
+}
+
+void launch_filter_coverage(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
+    if (n <= 0) return;
+    const int64_t n4 = (n + 3) / 4, grid = (n4 + kThreads - 1) / kThreads;
+    k_filter<true><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
+                                                       (const uint4*)t.flagmq, n, p, (int4*)c0, (int4*)c1, sc);
+}
+
+void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s) {
+    if (n_tiles <= 0) return;
+    const int64_t grid = (n_tiles + kThreads - 1) / kThreads;
+    k_join<<<unsigned(grid), kThreads, 0, s>>>(t, n, tiles, n_tiles, sc, const_cast<DeviceScalars*>(sc));
+}
+
+void launch_count(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int ss, int32_t* out,
+                  DeviceScalars*, cudaStream_t s) {
+    if (n_tiles <= 0) return;
+    const int64_t grid = (n_tiles * 32 + kThreads - 1) / kThreads;
+    k_count<<<unsigned(grid), kThreads, 0, s>>>(tiles, n_tiles, c0, c1, ss, out);
+}
+
+void launch_profile(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int ss, int32_t binsize,
+                    int max_tile_ints, int32_t* out, DeviceScalars*, cudaStream_t s) {
+    if (n_tiles <= 0) return;
+    uint64_t magic; uint32_t mshift;
+    magic_for(binsize, &magic, &mshift);
+    const size_t smem = size_t(max_tile_ints + 4) * sizeof(int32_t);
+    const unsigned grid = unsigned(n_tiles);
+    const bool agg = binsize >= 4;
+#define BSG_LAUNCH_PROFILE(SS, B1, AG) \
+    k_profile<SS, B1, AG><<<grid, kThreads, smem, s>>>(tiles, c0, c1, binsize, magic, mshift, out)
+    if (binsize == 1) { if (ss) BSG_LAUNCH_PROFILE(true, true, false); else BSG_LAUNCH_PROFILE(false, true, false); }
+    else if (agg)     { if (ss) BSG_LAUNCH_PROFILE(true, false, true); else BSG_LAUNCH_PROFILE(false, false, true); }
+    else              { if (ss) BSG_LAUNCH_PROFILE(true, false, false); else BSG_LAUNCH_PROFILE(false, false, false); }
+#undef BSG_LAUNCH_PROFILE
+}
+
+void launch_coverage(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int max_tile_ints,
+                     int32_t* out, DeviceScalars*, cudaStream_t s) {
+    if (n_tiles <= 0) return;
+    const size_t smem = size_t(max_tile_ints + 8) * sizeof(int32_t);
+    k_coverage<<<unsigned(n_tiles), kThreads, smem, s>>>(tiles, c0, c1, out);
+}
+
+}  // namespace bsg

@@ -1,0 +1,81 @@
+// Device-side data layout and kernel launchers of the counting path (sm_100a).
+//
+// HBM layout (all arrays cudaMalloc-aligned, SoA so that every kernel's loads and stores are coalesced):
+//   raw batch      uint8  raw[]         uncompressed BAM record bytes of one staged batch (+16 B slack)
+//                  uint32 offs[n+1]     byte offset of every record's block_size field; offs[n] = end of last record
+//   read table     int32  tid[N] pos[N] end[N] tlen[N], uint32 flagmq[N]   (20 B / read; end = 0-based inclusive
+//                                       alignment end = bam_endpos - 1; flagmq = flag | mapq << 16)
+//   coordinates    int32  c0[N] c1[N]   (8 B / read) pileup: c0 = 5'/midpoint coordinate, c1 = 0 '+', 1 '-', -1 dropped
+//                                       coverage: [c0,c1] = inclusive interval, dropped reads get c0 > c1 sentinels
+//   tiles          int32  rid loc len strand, int64 out_off, int64 cand_lo cand_hi   one row per region tile
+//   result         int32  out[]         flat, bsg_output_layout() order; every element written exactly once
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsg {
+
+struct ReadTable {
+    int32_t* tid;
+    int32_t* pos;
+    int32_t* end;
+    int32_t* tlen;
+    uint32_t* flagmq;
+};
+
+struct TileTable {
+    const int32_t* rid;
+    const int32_t* loc;
+    const int32_t* len;
+    const int32_t* strand;
+    const int64_t* out_off;
+    int64_t* cand_lo;
+    int64_t* cand_hi;
+};
+
+struct FilterParams {   // Pileupper / Coverager fields, src/bamsignals.cpp:296-303, :369-373
+    int32_t mapqual;
+    uint32_t required;
+    uint32_t filtered;
+    int32_t have_tlen, tmin, tmax;
+    int32_t midpoint, shift;   // pileup
+    int32_t tspan;             // coverage
+};
+
+// Device scalars shared by the kernels of one call.
+struct DeviceScalars {
+    int32_t halo_lo;     // pileup: max(c0 - pos) over kept reads; coverage: max(c1 - pos)
+    int32_t halo_hi;     // pileup: max(pos - c0);                coverage: max(pos - c0)
+    uint32_t status;     // bit 0: unsorted input, bit 1: corrupt record
+    uint32_t pad;
+    unsigned long long kept;
+    unsigned long long candidates;
+};
+enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u };
+
+constexpr int kTileInts = 8192;   // int32 per counting tile (32 KiB of shared memory)
+
+// K1: raw record bytes -> read table rows [row0, row0 + n).  Replaces bam_read1's field extraction and
+// bam_endpos (src/bamsignals.cpp:16-18).
+void launch_decode(const uint8_t* raw, const uint32_t* offs, int64_t n, int64_t row0, ReadTable t,
+                   DeviceScalars* sc, cudaStream_t s);
+
+// K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415).
+void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
+void launch_filter_coverage(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
+
+// K3: per tile, binary-search the (tid,pos)-sorted table for the candidate row range (the job of the sort + chunk
+// + sweep in overlapAndPileup, src/bamsignals.cpp:246-285).
+void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s);
+
+// K4: bamCount (one or two counters per region; Pileupper::pileup with every read in bin 0, :349-363, :162-167)
+void launch_count(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int ss, int32_t* out,
+                  DeviceScalars* sc, cudaStream_t s);
+// K4: bamProfile (shared-memory bin histogram per tile; Pileupper::pileup, :349-363)
+void launch_profile(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int ss, int32_t binsize,
+                    int max_tile_ints, int32_t* out, DeviceScalars* sc, cudaStream_t s);
+// K5: bamCoverage (shared-memory difference array + block scan; Coverager::pileup + cumsum, :418-438, :464-470)
+void launch_coverage(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int max_tile_ints,
+                     int32_t* out, DeviceScalars* sc, cudaStream_t s);
+
+}  // namespace bsg

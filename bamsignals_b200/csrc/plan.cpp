@@ -1,0 +1,138 @@
+#include "plan.h"
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+
+namespace bsg {
+
+void resolve_regions(const BamFile& bam, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                     const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                     Regions* out) {
+    if (R < 0 || (R > 0 && (!seq_idx || !loc || !width || !strand || !seq_levels))) fail(BSG_EARG, "invalid region arrays");
+    std::vector<int> level_rid(size_t(std::max(n_levels, 0)), -2);
+    out->R = R;
+    out->rid.resize(R); out->loc.assign(loc, loc + R); out->width.assign(width, width + R); out->strand.assign(strand, strand + R);
+    for (int64_t i = 0; i < R; ++i) {
+        const int lv = seq_idx[i];
+        if (lv < 0 || lv >= n_levels) fail(BSG_EARG, "region refers to a seqlevel index out of range");
+        if (level_rid[lv] == -2) {
+            level_rid[lv] = bam.name2id(seq_levels[lv]);                                      // getRefId, :26-28
+            if (level_rid[lv] < 0)
+                fail(BSG_ENOCHROM, std::string("chromosome ") + seq_levels[lv] + " not present in the bam file");   // :119
+        }
+        if (width[i] < 0) fail(BSG_EARG, "negative region width");
+        out->rid[i] = level_rid[lv];
+    }
+}
+
+void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int64_t* out_offsets, int tile_ints,
+                HostTiles* t) {
+    const int64_t R = rg.R;
+    const int mult = ss ? 2 : 1;
+    std::vector<int64_t> order(R);
+    std::iota(order.begin(), order.end(), int64_t(0));
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        return rg.rid[a] != rg.rid[b] ? rg.rid[a] < rg.rid[b] : (rg.loc[a] != rg.loc[b] ? rg.loc[a] < rg.loc[b] : a < b);
+    });
+    auto push = [&](int32_t rid, int64_t loc, int64_t len, int32_t strand, int64_t off, int64_t ints) {
+        t->rid.push_back(rid); t->loc.push_back(int32_t(loc)); t->len.push_back(int32_t(len));
+        t->strand.push_back(strand); t->out_off.push_back(off);
+        t->max_tile_ints = std::max<int64_t>(t->max_tile_ints, ints);
+    };
+    for (int64_t oi = 0; oi < R; ++oi) {
+        const int64_t i = order[oi];
+        const int64_t loc = rg.loc[i], width = rg.width[i], base = out_offsets[i];
+        const int32_t strand = rg.strand[i];
+        if (mode == MODE_COUNT) { push(rg.rid[i], loc, width, strand, base, mult); continue; }
+        if (width == 0) continue;
+        const int64_t bs = mode == MODE_COVERAGE ? 1 : binsize;
+        const int64_t m = mode == MODE_COVERAGE ? 1 : mult;
+        const int64_t nb = (width + bs - 1) / bs;
+        const int64_t tb = std::max<int64_t>(1, tile_ints / m);             // bins per tile
+        for (int64_t k = 0; k * tb < nb; ++k) {
+            const int64_t rel_lo = k * tb * bs, rel_hi = std::min(width, (k + 1) * tb * bs);
+            const int64_t tloc = strand < 0 ? loc + width - rel_hi : loc + rel_lo;
+            const int64_t bins = (rel_hi - rel_lo + bs - 1) / bs;
+            push(rg.rid[i], tloc, rel_hi - rel_lo, strand, base + m * k * tb, m * bins);
+        }
+    }
+}
+
+namespace {
+
+void scan_segment(const BamFile& bam, Segment* s) {
+    uint64_t c = s->vbeg >> 16;
+    const uint64_t cend = s->vend >> 16, uoff_end = s->vend & 0xffff;
+    s->ubeg = s->vbeg & 0xffff;
+    s->usize = 0; s->csize = 0;
+    bool closed = false;
+    for (;;) {
+        if (c == cend && uoff_end == 0) { s->uend = s->usize; closed = true; break; }
+        if (c > cend) break;
+        BlockInfo b;
+        if (!bam.block_at(c, &b)) break;
+        s->blocks.push_back(b);
+        s->usize += b.isize; s->csize += b.csize;
+        if (c == cend) {
+            if (uoff_end > b.isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam.path());
+            s->uend = s->usize - b.isize + uoff_end; closed = true; break;
+        }
+        c += b.csize;
+    }
+    if (!closed) fail(BSG_EFORMAT, "BAM index does not match the BGZF block structure of " + bam.path());
+    if (!s->blocks.empty() && s->ubeg > s->blocks[0].isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam.path());
+    if (s->blocks.empty()) { s->ubeg = s->uend = 0; }
+    if (s->ubeg > s->uend) fail(BSG_EFORMAT, "inconsistent index offsets in " + bam.path());
+}
+
+}  // namespace
+
+void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg_cbytes, Pool& pool,
+                std::vector<Segment>* segs) {
+    struct Q { int32_t rid; int64_t beg, end; };
+    std::vector<Q> qs;
+    qs.reserve(rg.R);
+    for (int64_t i = 0; i < rg.R; ++i) {
+        if (rg.width[i] == 0) continue;
+        const int64_t b = std::max<int64_t>(0, int64_t(rg.loc[i]) - ext), e = int64_t(rg.loc[i]) + rg.width[i] + ext;
+        if (e > b) qs.push_back(Q{rg.rid[i], b, e});
+    }
+    std::sort(qs.begin(), qs.end(), [](const Q& a, const Q& b) { return a.rid != b.rid ? a.rid < b.rid : a.beg < b.beg; });
+    std::vector<VRange> ranges;
+    for (size_t i = 0; i < qs.size();) {
+        Q cur = qs[i];
+        size_t j = i + 1;
+        for (; j < qs.size() && qs[j].rid == cur.rid && qs[j].beg <= cur.end + 16384; ++j) cur.end = std::max(cur.end, qs[j].end);
+        bam.query(cur.rid, cur.beg, cur.end, &ranges);
+        i = j;
+    }
+    std::sort(ranges.begin(), ranges.end(), [](const VRange& a, const VRange& b) { return a.beg < b.beg; });
+    std::vector<VRange> merged;
+    for (const VRange& r : ranges) {
+        if (r.end <= r.beg) continue;
+        if (!merged.empty() && r.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, r.end);
+        else merged.push_back(r);
+    }
+    const std::vector<uint64_t>& ent = bam.entry_points();
+    for (const VRange& r : merged) {
+        uint64_t cur = r.beg;
+        auto it = std::upper_bound(ent.begin(), ent.end(), cur);
+        for (; it != ent.end() && *it < r.end; ++it)
+            if ((*it >> 16) - (cur >> 16) >= seg_cbytes) {
+                Segment s; s.vbeg = cur; s.vend = *it; segs->push_back(std::move(s));
+                cur = *it;
+            }
+        Segment s; s.vbeg = cur; s.vend = r.end; segs->push_back(std::move(s));
+    }
+    std::mutex em; Error first{0, ""};
+    pool.parallel_for(int64_t(segs->size()), 1, [&](int64_t a, int64_t b, int) {
+        for (int64_t k = a; k < b; ++k) {
+            try { scan_segment(bam, &(*segs)[k]); }
+            catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }
+        }
+    });
+    if (first.code) throw first;
+}
+
+}  // namespace bsg

@@ -1,0 +1,133 @@
+/* bamsignals_cuda.h — C ABI of libbamsignals_cuda.so, the B200-native counting path of bamsignals.
+ *
+ * This is the drop-in boundary: the two entry points below are what the reference's R/Rcpp glue binds instead of its
+ * own per-region htslib loops.  Citations are relative to the reference tree (lamortenera/bamsignals):
+ *
+ *   bsg_pileup    replaces  overlapAndPileup<Pileupper>  called from pileup_core    src/bamsignals.cpp:444-461
+ *                           (.Call symbol bamsignals_pileup_core, src/RcppExports.cpp:34-52, src/bamsignals_init.c:15)
+ *   bsg_coverage  replaces  overlapAndPileup<Coverager> + cumsum in coverage_core   src/bamsignals.cpp:474-494
+ *                           (.Call symbol bamsignals_coverage_core, src/RcppExports.cpp:55-70, src/bamsignals_init.c:16)
+ *
+ * Plain C types only; nothing here depends on R, Rcpp, torch or htslib.  The caller (the R shim in rshim/, or the
+ * Python mirror bamsignals_b200/api.py) keeps doing what touches its own objects — parseRegions (S4 slots ->
+ * arrays, src/bamsignals.cpp:92-135) and allocateList (result vectors, :139-192) — and hands flat arrays over.
+ *
+ * Regions are parallel arrays of length R in the caller's order:
+ *   seq_levels[n_levels]  chromosome names (the factor levels of seqnames(gr)); looked up in the BAM header by NAME
+ *   seq_idx[i]            index into seq_levels
+ *   loc[i]                0-based start (= start(gr)[i] - 1, src/bamsignals.cpp:131)
+ *   width[i]              number of bases
+ *   strand[i]             +1 '+', -1 '-', 0 '*'
+ * tlen_filter is NULL (no TLEN filter; R passes integer()) or two ints {min,max} (src/bamsignals.cpp:330-332).
+ *
+ * Output: the library OVERWRITES every output element (no reliance on zero-fill).  Two ways to receive it:
+ *   out + out_offsets : one flat int32 buffer; region i occupies [out_offsets[i], out_offsets[i+1]) with
+ *                       bsg_output_layout()'s layout: bamCount (binsize <= 0): mult ints per region, i.e. the R
+ *                       IntegerVector(R) / column-major IntegerMatrix(2,R) (:148-169); otherwise mult*ceil(width/binsize)
+ *                       ints, interleaved [sense_0, antisense_0, sense_1, ...] when ss (:172-191).  mult = ss ? 2 : 1.
+ *   out_ptrs          : R pointers, out_ptrs[i] receives region i's slice (the R shim passes INTEGER(sig_i));
+ *                       used when `out` is NULL.  out_offsets is still required (it carries the sizes).
+ *
+ * Errors: functions return 0 or a negative BSG_E* code; bsg_last_error() returns the message (thread-local).  The
+ * messages for BSG_EOPEN / BSG_ENOINDEX / BSG_ENOCHROM are the reference's own Rcpp::stop strings
+ * (src/bamsignals.cpp:204, :209, :119) so the shim can re-raise them verbatim.  Nothing throws across the boundary,
+ * nothing calls back into the caller, all helper threads are joined before return.
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns BSG_ECUDA.
+ */
+#ifndef BAMSIGNALS_CUDA_H
+#define BAMSIGNALS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSG_OK         0
+#define BSG_EOPEN     -1   /* "Fail to open BAM file <path>" */
+#define BSG_ENOINDEX  -2   /* "BAM indexing file is not available for file <path>" */
+#define BSG_ENOCHROM  -3   /* "chromosome <name> not present in the bam file" */
+#define BSG_EFORMAT   -4   /* corrupt BGZF / BAM / BAI (bad magic, CRC, ISIZE, truncated record) */
+#define BSG_EUNSORTED -5   /* records not coordinate-sorted */
+#define BSG_ECUDA     -6   /* no device, launch or runtime failure */
+#define BSG_ENOMEM    -7   /* host or device allocation failed */
+#define BSG_EARG      -8   /* invalid argument ("negative 'ext' values don't make sense", :243, ...) */
+
+/* Execution options; none of them changes results.  Zero-initialise, set struct_size = sizeof(bsg_opts). */
+typedef struct bsg_opts {
+    int32_t struct_size;
+    int32_t n_devices;        /* 0 = use device 0 only; >0 = devices[0..n) (regions sharded, no collective) */
+    int32_t devices[16];
+    int32_t inflate_threads;  /* host inflate / record-walk workers; 0 = all hardware threads */
+    int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (64 MiB) */
+    int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does) */
+    int32_t use_cache;        /* keep the decoded read table of the last BAM resident in HBM across calls */
+    int32_t gpu_inflate;      /* 1 = inflate BGZF blocks on the device (host ships compressed bytes) */
+    int32_t reserved[8];
+} bsg_opts;
+
+/* Counters and timings of the last call on this thread (milliseconds; kernel times from CUDA events on the
+ * launching stream, summed over launches and max over devices). */
+typedef struct bsg_timings {
+    int64_t records;          /* alignment records decoded (inside the fetched ranges) */
+    int64_t records_kept;     /* records that passed the mapq/flag/tlen filter */
+    int64_t bytes_compressed; /* BGZF bytes read */
+    int64_t bytes_inflated;   /* uncompressed bytes produced */
+    int64_t candidates;       /* (read, tile) pairs examined by the counting kernels */
+    int64_t out_elems;        /* int32 written to the result */
+    int64_t n_tiles;
+    int64_t n_batches;
+    int64_t n_launches;       /* kernels launched by this library during the call */
+    int32_t n_devices;
+    int32_t pad;
+    double ms_total, ms_plan, ms_fetch, ms_h2d, ms_d2h;
+    double ms_decode, ms_filter, ms_join, ms_count, ms_inflate_gpu, ms_kernels;
+    double ms_device;         /* first to last device event of the call on the compute stream (kernels + gaps) */
+    double reserved[7];
+} bsg_timings;
+
+/* bamCount (binsize <= 0) and bamProfile (binsize >= 1).  Argument order follows pileup_core
+ * (src/bamsignals.cpp:444-446); maxgap is accepted for signature parity and ignored (it only prunes I/O). */
+int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+               const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+               const int32_t* tlen_filter, int32_t mapqual, int32_t binsize, int32_t shift, int32_t ss,
+               int32_t requiredF, int32_t filteredF, int32_t pe_mid, int32_t maxgap,
+               int32_t* out, const int64_t* out_offsets, int32_t* const* out_ptrs, const bsg_opts* opts);
+
+/* bamCoverage.  Argument order follows coverage_core (src/bamsignals.cpp:474-476). */
+int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                 const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                 const int32_t* tlen_filter, int32_t mapqual, int32_t requiredF, int32_t filteredF, int32_t tspan,
+                 int32_t maxgap, int32_t* out, const int64_t* out_offsets, int32_t* const* out_ptrs,
+                 const bsg_opts* opts);
+
+/* allocateList's sizes (src/bamsignals.cpp:139-192): fills offsets[0..R], returns the total element count. */
+int64_t bsg_output_layout(int64_t R, const int32_t* width, int32_t binsize, int32_t ss, int64_t* offsets);
+
+/* ---- resident sessions: stage once, count many times -------------------------------------------------------------
+ * bsg_stage() fetches, inflates and uploads the byte ranges a region set needs and keeps the RAW record bytes and
+ * record offsets resident in HBM.  bsg_pileup_staged()/bsg_coverage_staged() then run the device path only
+ * (decode -> filter -> join -> count) and leave the result on the device unless `out` is given.  This is how the
+ * kernel-only throughput is measured, and how an application amortises inflate over many parameter settings. */
+typedef struct bsg_stage bsg_stage;
+int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                   const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                   int32_t ext_hint, const bsg_opts* opts);
+int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t binsize, int32_t shift,
+                      int32_t ss, int32_t requiredF, int32_t filteredF, int32_t pe_mid,
+                      int32_t* out, const int64_t* out_offsets);
+int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t requiredF,
+                        int32_t filteredF, int32_t tspan, int32_t* out, const int64_t* out_offsets);
+void bsg_stage_close(bsg_stage* st);
+
+const char* bsg_last_error(void);          /* valid until the next call on this thread */
+int  bsg_get_timings(bsg_timings* t);      /* of the last call on this thread */
+int  bsg_device_count(void);               /* CUDA devices visible (0 if none) */
+void bsg_shutdown(void);                   /* release cached device / pinned memory and worker threads */
+const char* bsg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMSIGNALS_CUDA_H */

@@ -1,0 +1,159 @@
+"""GPU parity beyond the reference fixture: scaled-down versions of BASELINE.json's configs C2..C5 from the synthetic
+generator, hand-crafted edge-case BAMs (CIGAR variety, flag-0x4 reads, straddling records, unsorted / corrupt
+input), batching and threading options that must not change results."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import bamsignals_b200 as B
+import bamwriter as W
+import edge_cases as E
+import oracle_api as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import workloads as WL  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and np.array_equal(x, y)
+
+
+@pytest.fixture(scope="module")
+def gen_dir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("gen"))
+
+
+@pytest.mark.parametrize("preset,gs,record", [("c2", 0.002, "compact"), ("c2", 0.001, "realistic"), ("c3", 0.004, "compact"),
+                                              ("c3", 0.002, "realistic"), ("c4", 0.002, "compact"), ("c5", 0.002, "compact")])
+def test_scaled_configs(gen_dir, preset, gs, record):
+    bam, info = WL.make_bam(preset, gs, gen_dir, record=record, unplaced=7)
+    gr, kw, fn = WL.regions(preset, gs)
+    got = getattr(B, fn)(bam, gr, **kw)
+    t = B.timings()
+    want = getattr(O, fn)(bam, gr, nthreads=8, **kw)
+    assert np.array_equal(WL.as_flat(got), WL.as_flat(want))
+    assert t["records"] > 0 and t["records"] <= info["records"]
+    assert int(WL.as_flat(got).sum()) > 0
+
+
+@pytest.mark.parametrize("batch_bytes,threads", [(1 << 16, 1), (1 << 20, 3), (1 << 22, 0)])
+def test_batching_does_not_change_results(gen_dir, batch_bytes, threads):
+    bam, _ = WL.make_bam("c4", 0.002, gen_dir, unplaced=7)
+    gr, kw, fn = WL.regions("c4", 0.002)
+    ref = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch_bytes, inflate_threads=threads), **kw)
+    assert np.array_equal(WL.as_flat(got), ref)
+    assert B.timings()["n_batches"] >= (2 if batch_bytes < (1 << 22) else 1)
+
+
+def test_all_apis_on_paired_synthetic(gen_dir):
+    """Every paired.end mode on a paired-end synthetic BAM with soft clips, indels, splices and flag-0x4 mates."""
+    bam, _ = WL.make_bam("c3", 0.004, gen_dir)
+    rng = np.random.default_rng(9)
+    n = 300
+    L = WL.contig_lens("c3", 0.004)[0]
+    gr = B.GRanges(["chr1"] * n, rng.integers(1, L - 20000, n), rng.integers(1, 20000, n), rng.choice(["+", "-", "*"], n).tolist())
+    for pe in ("ignore", "filter", "midpoint"):
+        for tf in (None, (100, 400)):
+            kw = dict(paired_end=pe, tlenFilter=tf, shift=13, mapqual=5)
+            assert np.array_equal(B.bamCount(bam, gr, ss=True, **kw), O.bamCount(bam, gr, ss=True, **kw))
+            same(B.bamProfile(bam, gr, binsize=1, ss=True, **kw).as_list(), O.bamProfile(bam, gr, binsize=1, ss=True, **kw).as_list())
+    for pe in ("ignore", "extend"):
+        for ff in (-1, 1024, 4):
+            same(B.bamCoverage(bam, gr, paired_end=pe, filteredFlag=ff).as_list(), O.bamCoverage(bam, gr, paired_end=pe, filteredFlag=ff).as_list())
+
+
+@pytest.mark.parametrize("straddle", [False, True])
+def test_cigar_and_flag_variety(tmp_path, straddle):
+    p = str(tmp_path / "v.bam")
+    E.write_variety(p, block_payload=997, cut_mid_record=straddle)
+    gr = E.variety_regions()
+    for kw in (dict(), dict(ss=True, shift=33), dict(paired_end="midpoint", tlenFilter=(0, 500), ss=True),
+               dict(filteredFlag=1024, mapqual=20), dict(filteredFlag=4), dict(filteredFlag=20)):
+        assert np.array_equal(B.bamCount(p, gr, **kw), O.bamCount(p, gr, **kw)), kw
+    for kw in (dict(binsize=1, ss=True), dict(binsize=50, shift=-20), dict(binsize=7, ss=True, paired_end="filter")):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            same(B.bamProfile(p, gr, **kw).as_list(), O.bamProfile(p, gr, **kw).as_list())
+    for kw in (dict(), dict(paired_end="extend", tlenFilter=(0, 600)), dict(mapqual=59)):
+        same(B.bamCoverage(p, gr, **kw).as_list(), O.bamCoverage(p, gr, **kw).as_list())
+
+
+def test_long_cigar_placeholder(tmp_path):
+    p = str(tmp_path / "cg.bam")
+    W.write_bam(p, [("chrA", 200000)], [E.long_cigar_read()])
+    gr = B.GRanges(["chrA"] * 2, [1, 60000], [100000, 20000], ["+", "-"])
+    same(B.bamCoverage(p, gr).as_list(), O.bamCoverage(p, gr).as_list())
+    assert B.bamCount(p, gr).tolist() == O.bamCount(p, gr).tolist() == [1, 0]
+    assert B.bamCount(p, gr, ss=True, shift=0).tolist() == O.bamCount(p, gr, ss=True).tolist()
+
+
+def test_empty_bam_and_empty_chromosome(tmp_path):
+    p = str(tmp_path / "empty.bam")
+    W.write_bam(p, [("chrA", 1000), ("chrB", 1000)], [])
+    gr = B.GRanges(["chrA", "chrB"], [1, 10], [100, 50], ["+", "-"])
+    assert B.bamCount(p, gr, ss=True).tolist() == [[0, 0], [0, 0]]
+    assert all(int(x.sum()) == 0 for x in B.bamProfile(p, gr).as_list())
+    assert [len(x) for x in B.bamCoverage(p, gr).as_list()] == [100, 50]
+    p2 = str(tmp_path / "one.bam")
+    W.write_bam(p2, [("chrA", 1000), ("chrB", 1000)], [dict(tid=1, pos=20, flag=16, mapq=9, cigar="10M", tlen=0)])
+    assert B.bamCount(p2, gr, ss=True).tolist() == O.bamCount(p2, gr, ss=True).tolist()
+    same(B.bamCoverage(p2, gr).as_list(), O.bamCoverage(p2, gr).as_list())
+
+
+def test_unsorted_input_is_an_error(tmp_path):
+    p = str(tmp_path / "unsorted.bam")
+    reads = [dict(tid=0, pos=x, flag=0, mapq=30, cigar="20M", tlen=0) for x in (100, 500, 300, 900)]
+    W.write_bam(p, [("chrA", 5000)], reads)
+    with pytest.raises(B.BamsignalsError) as e:
+        B.bamCount(p, B.GRanges(["chrA"], [1], [5000]))
+    assert e.value.code == -5
+
+
+def test_corrupt_bgzf_is_an_error(tmp_path, fixture_bam):
+    raw = bytearray(open(fixture_bam, "rb").read())
+    raw[200000] ^= 0xFF                                   # inside some block's deflate stream
+    p = str(tmp_path / "corrupt.bam")
+    open(p, "wb").write(raw)
+    open(p + ".bai", "wb").write(open(fixture_bam + ".bai", "rb").read())
+    gr = B.GRanges(["chr1", "chr2", "chr3"], [1, 1, 1], [10000] * 3)
+    with pytest.raises(B.BamsignalsError) as e:
+        B.bamCount(p, gr)
+    assert e.value.code == -4
+    open(p, "wb").write(raw[:700000])                     # truncated mid-block
+    with pytest.raises(B.BamsignalsError) as e:
+        B.bamCount(p, gr)
+    assert e.value.code == -4
+    # the library is still usable after an error
+    assert np.array_equal(B.bamCount(fixture_bam, gr), O.bamCount(fixture_bam, gr))
+
+
+def test_properties_at_scale(gen_dir):
+    """Size-independent properties on a larger input than the oracle is asked to check bin by bin:
+    profile sums == counts, ss rows sum to the unstranded profile, coverage of + and - regions mirror each other,
+    filteredFlag=0 gives zeros, binned profile == reshaped sum of the bp profile."""
+    bam, info = WL.make_bam("c2", 0.02, gen_dir)
+    gr, kw, _ = WL.regions("c2", 0.02)
+    prof = B.bamProfile(bam, gr, **kw)
+    cnt = B.bamCount(bam, gr, ss=True, shift=75)
+    assert np.array_equal(np.stack([p.sum(axis=1) for p in prof.as_list()], axis=1), cnt)
+    uns = B.bamProfile(bam, gr, binsize=1, ss=False, shift=75).alignSignals()
+    assert np.array_equal(prof.alignSignals().sum(axis=0), uns)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b40 = B.bamProfile(bam, gr, binsize=40, ss=False, shift=75).alignSignals()
+    assert np.array_equal(uns.reshape(50, 40, -1).sum(axis=1), b40)
+    assert int(B.bamCount(bam, gr, filteredFlag=0).sum()) == 0
+    flipped = B.GRanges.from_codes(gr.seqlevels, gr.seq_idx, gr.start, gr.width, -gr.strand)
+    c1 = B.bamCoverage(bam, gr).alignSignals()
+    c2 = B.bamCoverage(bam, flipped).alignSignals()
+    assert np.array_equal(c1, c2[::-1])
+    assert B.timings()["records"] > 0.5 * info["records"]

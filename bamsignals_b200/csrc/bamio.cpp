@@ -157,6 +157,12 @@ void BamFile::load_index() {
         uint8_t tmp[1 << 16];
         size_t k;
         while ((k = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + k);
+        struct stat st;
+        if (fstat(fileno(fp), &st) == 0) {
+            index_size_ = uint64_t(st.st_size);
+            index_mtime_ns_ = uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec);
+        }
+        index_path_ = c;
         fclose(fp);
         found = true;
         break;
@@ -211,6 +217,13 @@ void BamFile::load_index() {
     entries_.erase(std::unique(entries_.begin(), entries_.end()), entries_.end());
     // Normalise "end of block" offsets: (coff, usize) and (coff_next, 0) denote the same position; both forms stay
     // in the list (they differ numerically) which is harmless: the planner resolves positions through block tables.
+}
+
+bool BamFile::index_unchanged() const {
+    struct stat st;
+    if (::stat(index_path_.c_str(), &st) != 0) return false;
+    return uint64_t(st.st_size) == index_size_ &&
+           uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec) == index_mtime_ns_;
 }
 
 static void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t>& out) {

@@ -51,6 +51,7 @@ public:
 
     // Identity of the file contents for the resident-table cache.
     uint64_t mtime_ns() const { return mtime_ns_; }
+    bool index_unchanged() const;   // the .bai on disk still has the size and mtime it had when it was parsed
 
 private:
     struct RefIndex {
@@ -65,6 +66,8 @@ private:
     const uint8_t* data_ = nullptr;
     uint64_t size_ = 0;
     uint64_t mtime_ns_ = 0;
+    std::string index_path_;
+    uint64_t index_size_ = 0, index_mtime_ns_ = 0;
     std::vector<std::string> names_;
     std::vector<int32_t> lens_;
     std::unordered_map<std::string, int> name2id_;

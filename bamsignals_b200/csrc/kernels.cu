@@ -23,77 +23,157 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1 decode.  One thread per record.  Records start at arbitrary byte offsets, so every field is assembled from
-// aligned 32-bit words with a funnel shift; neighbouring threads read neighbouring records, so the words come from
-// the same few 128-byte lines (L1 absorbs the overlap, DRAM sees each byte once).
+// K1 decode.  One CTA per chunk of 256 consecutive records, one thread per record.
+//
+// Records start at arbitrary byte offsets, so a per-thread gather from global memory makes every load instruction
+// touch a dozen 128-byte lines (measured: 15 % of HBM peak).  Instead the CTA's records are one CONTIGUOUS byte span
+// [offs[i0], offs[i0+256]) of the batch: thread 0 issues a single TMA bulk copy (cp.async.bulk, completion on an
+// mbarrier) of that span into shared memory, so DRAM is read in full lines exactly once, and the threads then pick
+// their fields out of shared memory with aligned 32-bit loads + funnel shifts.  Eight CTAs are resident per SM, so
+// the copy of one chunk overlaps the decode and the coalesced SoA stores of the others.  Spans that do not fit the
+// shared buffer (records with long SEQ/QUAL: only ~60 of their bytes are needed) take the direct global-load path.
+//
 // Fixed part of a record (offsets from the block_size field): refID +4, pos +8, l_read_name +12, mapq +13,
 // bin +14, n_cigar_op +16, flag +18, l_seq +20, next_refID +24, next_pos +28, tlen +32, read_name +36, cigar after.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_decode(const uint8_t* __restrict__ raw, const uint32_t* __restrict__ offs,
-                                                     int n, int64_t row0, ReadTable t, DeviceScalars* sc) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    const bool active = i < n;
-    int32_t tid = -1, pos = -1;
-    uint32_t bad = 0;
-    if (active) {
-        const uint32_t o = offs[i];
-        const uint32_t rec_end = offs[i + 1];
-        const uint32_t a = o + 4;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (a & ~3u));
-        const uint32_t sh = (a & 3u) * 8;
-        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
-        const uint32_t w7 = __ldg(w + 7), w8 = __ldg(w + 8);
-        tid = int32_t(__funnelshift_r(w0, w1, sh));
-        pos = int32_t(__funnelshift_r(w1, w2, sh));
-        const uint32_t nm = __funnelshift_r(w2, w3, sh);   // l_read_name | mapq << 8 | bin << 16
-        const uint32_t cf = __funnelshift_r(w3, w4, sh);   // n_cigar_op | flag << 16
-        const int32_t tlen = int32_t(__funnelshift_r(w7, w8, sh));
-        const uint32_t l_name = nm & 0xffu, mapq = (nm >> 8) & 0xffu;
-        const uint32_t n_cigar = cf & 0xffffu, flag = cf >> 16;
-        const uint32_t c = o + 36 + l_name;
-        uint32_t rlen = 0;
-        if (c + 4u * n_cigar > rec_end) {
-            bad = STATUS_CORRUPT;
-        } else if (!(flag & 0x4u) && n_cigar) {             // bam_endpos: unmapped reads have no reference length
-            const uint32_t* cw = reinterpret_cast<const uint32_t*>(raw + (c & ~3u));
-            const uint32_t csh = (c & 3u) * 8;
-            uint32_t lo = __ldg(cw);
-            for (uint32_t k = 0; k < n_cigar; ++k) {
-                const uint32_t hi = __ldg(cw + k + 1);
-                const uint32_t op = __funnelshift_r(lo, hi, csh);
-                lo = hi;
-                if ((0x18Du >> (op & 0xfu)) & 1u) rlen += op >> 4;   // M, D, N, =, X consume the reference
-            }
+constexpr int kSpanCap = 24 * 1024;   // bytes of shared staging per CTA (average record <= 96 B)
+
+struct GlobalLd {
+    const uint8_t* raw;
+    __device__ __forceinline__ uint32_t operator()(uint32_t aligned_off) const {
+        return __ldg(reinterpret_cast<const uint32_t*>(raw + aligned_off));
+    }
+};
+struct SharedLd {
+    const uint8_t* sm;
+    uint32_t lo;
+    __device__ __forceinline__ uint32_t operator()(uint32_t aligned_off) const {
+        return *reinterpret_cast<const uint32_t*>(sm + (aligned_off - lo));
+    }
+};
+
+struct Decoded {
+    int32_t tid, pos, end, tlen;
+    uint32_t flagmq, bad;
+};
+
+template <class LD>
+__device__ __forceinline__ Decoded decode_one(const LD& ld, uint32_t o, uint32_t rec_end) {
+    Decoded d;
+    const uint32_t a = o + 4, b = a & ~3u, sh = (a & 3u) * 8;
+    const uint32_t w0 = ld(b), w1 = ld(b + 4), w2 = ld(b + 8), w3 = ld(b + 12), w4 = ld(b + 16);
+    const uint32_t w7 = ld(b + 28), w8 = ld(b + 32);
+    d.tid = int32_t(__funnelshift_r(w0, w1, sh));
+    d.pos = int32_t(__funnelshift_r(w1, w2, sh));
+    const uint32_t nm = __funnelshift_r(w2, w3, sh);   // l_read_name | mapq << 8 | bin << 16
+    const uint32_t cf = __funnelshift_r(w3, w4, sh);   // n_cigar_op | flag << 16
+    d.tlen = int32_t(__funnelshift_r(w7, w8, sh));
+    const uint32_t l_name = nm & 0xffu, mapq = (nm >> 8) & 0xffu;
+    const uint32_t n_cigar = cf & 0xffffu, flag = cf >> 16;
+    const uint32_t c = o + 36 + l_name;
+    uint32_t rlen = 0;
+    d.bad = 0;
+    if (c + 4u * n_cigar > rec_end) {
+        d.bad = STATUS_CORRUPT;
+    } else if (!(flag & 0x4u) && n_cigar) {             // bam_endpos: unmapped reads have no reference length
+        const uint32_t cb = c & ~3u, csh = (c & 3u) * 8;
+        uint32_t lo = ld(cb);
+        for (uint32_t k = 0; k < n_cigar; ++k) {
+            const uint32_t hi = ld(cb + 4 * k + 4);
+            const uint32_t op = __funnelshift_r(lo, hi, csh);
+            lo = hi;
+            if ((0x18Du >> (op & 0xfu)) & 1u) rlen += op >> 4;   // M, D, N, =, X consume the reference
         }
-        if (rlen == 0) rlen = 1;
-        const int64_t row = row0 + i;
-        t.tid[row] = tid;
-        t.pos[row] = pos;
-        t.end[row] = int32_t(uint32_t(pos) + rlen - 1u);
-        t.tlen[row] = tlen;
-        t.flagmq[row] = flag | (mapq << 16);
+    }
+    if (rlen == 0) rlen = 1;
+    d.end = int32_t(uint32_t(d.pos) + rlen - 1u);
+    d.flagmq = flag | (mapq << 16);
+    return d;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const DecodeBatch* __restrict__ table,
+                                                     int n_batches, ReadTable t, DeviceScalars* sc) {
+    extern __shared__ __align__(128) uint8_t sm_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_lo, s_bytes;
+    // which batch does this chunk belong to?
+    DecodeBatch B = single;
+    if (table) {
+        int lo = 0, hi = n_batches - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (int(blockIdx.x) >= table[mid].chunk0) lo = mid; else hi = mid - 1;
+        }
+        B = table[lo];
+    }
+    const int i0 = (int(blockIdx.x) - B.chunk0) * kThreads;
+    const int i = i0 + threadIdx.x;
+    const bool active = i < B.n;
+    if (threadIdx.x == 0) {
+        const int i1 = min(i0 + kThreads, B.n);
+        const uint32_t o_lo = B.offs[i0], o_hi = B.offs[i1];
+        const uint32_t lo = o_lo & ~15u;
+        const uint32_t bytes = (o_hi - lo + 15u) & ~15u;
+        if (bytes <= uint32_t(kSpanCap)) {
+            const uint32_t bar_a = smem_u32(&bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sm_raw)), "l"(B.raw + lo), "r"(bytes), "r"(bar_a) : "memory");
+            s_lo = lo; s_bytes = bytes;
+        } else {
+            s_lo = 0; s_bytes = 0;
+        }
+    }
+    uint32_t o = 0, rec_end = 0;
+    if (active) { o = __ldg(B.offs + i); rec_end = __ldg(B.offs + i + 1); }   // in flight while the bulk copy lands
+    __syncthreads();
+    const bool staged = s_bytes != 0;
+    if (staged) {
+        const uint32_t bar_a = smem_u32(&bar);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a) : "memory");
+    }
+    Decoded d;
+    d.tid = -1; d.pos = -1; d.bad = 0;
+    const SharedLd sld{sm_raw, s_lo};
+    const GlobalLd gld{B.raw};
+    if (active) {
+        d = staged ? decode_one(sld, o, rec_end) : decode_one(gld, o, rec_end);
+        const int64_t row = B.row0 + i;
+        t.tid[row] = d.tid;
+        t.pos[row] = d.pos;
+        t.end[row] = d.end;
+        t.tlen[row] = d.tlen;
+        t.flagmq[row] = d.flagmq;
     }
     // coordinate-sortedness: compare with the previous record (previous lane; lane 0 re-reads it)
     const int lane = threadIdx.x & 31;
-    uint32_t ptid = __shfl_up_sync(FULL, uint32_t(tid), 1);
-    int32_t ppos = __shfl_up_sync(FULL, pos, 1);
+    uint32_t ptid = __shfl_up_sync(FULL, uint32_t(d.tid), 1);
+    int32_t ppos = __shfl_up_sync(FULL, d.pos, 1);
     bool have_prev = active;
     if (lane == 0 && active) {
         if (i > 0) {
-            const uint32_t a = offs[i - 1] + 4;
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (a & ~3u));
-            const uint32_t sh = (a & 3u) * 8;
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+            const uint32_t a = __ldg(B.offs + i - 1) + 4, b = a & ~3u, sh = (a & 3u) * 8;
+            uint32_t w0, w1, w2;
+            if (staged && threadIdx.x > 0) { w0 = sld(b); w1 = sld(b + 4); w2 = sld(b + 8); }
+            else { w0 = gld(b); w1 = gld(b + 4); w2 = gld(b + 8); }
             ptid = __funnelshift_r(w0, w1, sh);
             ppos = int32_t(__funnelshift_r(w1, w2, sh));
-        } else if (row0 > 0) {
-            ptid = uint32_t(t.tid[row0 - 1]);
-            ppos = t.pos[row0 - 1];
+        } else if (B.row0 > 0) {
+            ptid = uint32_t(t.tid[B.row0 - 1]);
+            ppos = t.pos[B.row0 - 1];
         } else {
             have_prev = false;
         }
     }
-    if (have_prev && (uint32_t(tid) < ptid || (uint32_t(tid) == ptid && pos < ppos))) bad |= STATUS_UNSORTED;
+    uint32_t bad = d.bad;
+    if (have_prev && (uint32_t(d.tid) < ptid || (uint32_t(d.tid) == ptid && d.pos < ppos))) bad |= STATUS_UNSORTED;
     if (bad) atomicOr(&sc->status, bad);
 }
 
@@ -394,11 +474,18 @@ void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
 
 }  // namespace
 
-void launch_decode(const uint8_t* raw, const uint32_t* offs, int64_t n, int64_t row0, ReadTable t, DeviceScalars* sc,
-                   cudaStream_t s) {
-    if (n <= 0) return;
-    const int64_t grid = (n + kThreads - 1) / kThreads;
-    k_decode<<<unsigned(grid), kThreads, 0, s>>>(raw, offs, int(n), row0, t, sc);
+void launch_decode(const DecodeBatch& one, ReadTable t, DeviceScalars* sc, cudaStream_t s) {
+    if (one.n <= 0) return;
+    const int grid = (one.n + kThreads - 1) / kThreads;
+    DecodeBatch b = one;
+    b.chunk0 = 0;
+    k_decode<<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, sc);
+}
+
+void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, DeviceScalars* sc,
+                         cudaStream_t s) {
+    if (n_batches <= 0 || total_chunks <= 0) return;
+    k_decode<<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, sc);
 }
 
 void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {

@@ -55,10 +55,22 @@ enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u };
 
 constexpr int kTileInts = 8192;   // int32 per counting tile (32 KiB of shared memory)
 
+// One staged batch of raw records for K1.
+struct DecodeBatch {
+    const uint8_t* raw;     // uncompressed record bytes (16-byte aligned, >= 64 bytes of slack behind the data)
+    const uint32_t* offs;   // n + 1 byte offsets into raw
+    int64_t row0;           // first read-table row of this batch
+    int32_t n;              // records
+    int32_t chunk0;         // first 256-record chunk of this batch in a multi-batch launch
+};
+constexpr int kDecodeChunk = 256;
+
 // K1: raw record bytes -> read table rows [row0, row0 + n).  Replaces bam_read1's field extraction and
-// bam_endpos (src/bamsignals.cpp:16-18).
-void launch_decode(const uint8_t* raw, const uint32_t* offs, int64_t n, int64_t row0, ReadTable t,
-                   DeviceScalars* sc, cudaStream_t s);
+// bam_endpos (src/bamsignals.cpp:16-18).  launch_decode: one batch (streaming path); launch_decode_table: every
+// resident batch of a staged session in ONE launch (d_table lives in device memory).
+void launch_decode(const DecodeBatch& one, ReadTable t, DeviceScalars* sc, cudaStream_t s);
+void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, DeviceScalars* sc,
+                         cudaStream_t s);
 
 // K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415).
 void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);

@@ -61,6 +61,8 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
 
 namespace {
 
+constexpr uint64_t kFuseGapCBytes = 1 << 16;   // compressed bytes
+
 void scan_segment(const BamFile& bam, Segment* s) {
     uint64_t c = s->vbeg >> 16;
     const uint64_t cend = s->vend >> 16, uoff_end = s->vend & 0xffff;
@@ -111,7 +113,10 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     std::vector<VRange> merged;
     for (const VRange& r : ranges) {
         if (r.end <= r.beg) continue;
-        if (!merged.empty() && r.beg <= merged.back().end) merged.back().end = std::max(merged.back().end, r.end);
+        // Ranges that touch the same or neighbouring BGZF blocks are fused: fetching is block-granular, so a gap
+        // shorter than a block would only make both neighbours inflate the shared blocks twice.
+        if (!merged.empty() && (r.beg >> 16) <= (merged.back().end >> 16) + kFuseGapCBytes)
+            merged.back().end = std::max(merged.back().end, r.end);
         else merged.push_back(r);
     }
     const std::vector<uint64_t>& ent = bam.entry_points();

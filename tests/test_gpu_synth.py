@@ -156,4 +156,4 @@ def test_properties_at_scale(gen_dir):
     c1 = B.bamCoverage(bam, gr).alignSignals()
     c2 = B.bamCoverage(bam, flipped).alignSignals()
     assert np.array_equal(c1, c2[::-1])
-    assert B.timings()["records"] > 0.5 * info["records"]
+    assert B.timings()["records"] > 0.3 * info["records"]

@@ -80,23 +80,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def shard_regions(gr, rank, world):
-    """Contiguous slice (in (chromosome, start) order) of the region set for this rank: region/tile independence
-     means no exchange step; every output element has exactly one owner."""
-    if world == 1:
-        return gr, np.arange(len(gr))
-    order = np.lexsort((gr.start, gr.seq_idx))
-    lo, hi = len(gr) * rank // world, len(gr) * (rank + 1) // world
-    idx = np.sort(order[lo:hi])
-    return gr[idx], idx
-
-
-def split_wide_regions(gr, world):
-    """C4 has 24 regions: cut each into bin-aligned '*'-strand pieces so that 8 ranks all get work.  Pieces are
-    independent regions whose outputs concatenate to the original (profile tiles)."""
-    return gr
-
-
 def run_ours(args, rank, world, local_rank):
     import bamsignals_b200 as B
     import torch
@@ -123,7 +106,7 @@ def run_ours(args, rank, world, local_rank):
         bam, info = WL.make_bam(preset, gs, d)
     t_gen = time.time() - t_gen
     gr_all, kw, fn = WL.regions(preset, gs)
-    gr, _ = shard_regions(gr_all, rank, world)
+    gr, _ = WL.shard_regions(gr_all, rank, world)
     ca = B.core_args(fn, **kw)
     opts = B.default_opts(devices=[local_rank])
     is_cov = fn == "bamCoverage"

@@ -91,3 +91,28 @@ def as_flat(result):
     if not sig:
         return np.zeros(0, np.int32)
     return np.concatenate([s.ravel(order="F") for s in sig])
+
+
+def shard_regions(gr, rank, world):
+    """Contiguous slice (in (chromosome, start) order) of the region set for this rank -> (GRanges, original indices).
+    Regions are independent: no exchange step, every output element has exactly one owner."""
+    if world == 1:
+        return gr, np.arange(len(gr))
+    order = np.lexsort((gr.start, gr.seq_idx))
+    lo, hi = len(gr) * rank // world, len(gr) * (rank + 1) // world
+    idx = np.sort(order[lo:hi])
+    return gr[idx], idx
+
+
+def merge_shards(parts, offsets):
+    """parts: [(idx, flat)] from every rank, each flat in the shard's own bsg_output_layout() order; offsets: the
+    full region set's layout (R+1).  Returns the full flat result."""
+    out = np.zeros(int(offsets[-1]), dtype=np.int32)
+    for idx, flat in parts:
+        pos = 0
+        for i in idx:
+            n = int(offsets[i + 1] - offsets[i])
+            out[offsets[i]:offsets[i + 1]] = flat[pos:pos + n]
+            pos += n
+        assert pos == len(flat)
+    return out

@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbamsignals_cuda.so")
+_LIB_PATH = os.environ.get("BSG_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbamsignals_cuda.so")
 _lib = None
 
 

@@ -219,6 +219,22 @@ void BamFile::load_index() {
     // in the list (they differ numerically) which is harmless: the planner resolves positions through block tables.
 }
 
+int64_t BamFile::bp_per_block(int tid) const {
+    if (tid < 0 || tid >= int(refs_.size()) || tid >= int(lens_.size())) return 16384;
+    auto meta = refs_[tid].bins.find(37450);
+    uint64_t beg = 0, end = 0;
+    if (meta != refs_[tid].bins.end() && !meta->second.empty()) { beg = meta->second[0].beg >> 16; end = meta->second[0].end >> 16; }
+    else {
+        const auto& lin = refs_[tid].linear;
+        for (uint64_t v : lin) if (v) { beg = v >> 16; break; }
+        for (size_t k = lin.size(); k-- > 0;) if (lin[k]) { end = lin[k] >> 16; break; }
+    }
+    if (end <= beg) return 16384;
+    const double cbytes_per_bp = double(end - beg) / double(std::max<int32_t>(1, lens_[tid]));
+    const double bp = 65536.0 / std::max(1e-9, cbytes_per_bp);
+    return int64_t(std::min(16.0e6, std::max(16384.0, bp)));
+}
+
 bool BamFile::index_unchanged() const {
     struct stat st;
     if (::stat(index_path_.c_str(), &st) != 0) return false;

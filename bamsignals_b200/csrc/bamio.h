@@ -45,6 +45,10 @@ public:
     // bins + linear-index rule), sorted and merged.  A superset is all the counting path needs.
     void query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out) const;
 
+    // Genomic distance (bp) on `tid` that one maximal BGZF block (64 KiB compressed) covers on average, from the
+    // index's (ref_beg, ref_end) file offsets: index queries closer than this fetch the same blocks anyway.
+    int64_t bp_per_block(int tid) const;
+
     // Sorted, de-duplicated record-aligned virtual offsets known to the index (linear index entries, chunk
     // begins/ends, first record): independent entry points for parallel inflate + record walking.
     const std::vector<uint64_t>& entry_points() const { return entries_; }

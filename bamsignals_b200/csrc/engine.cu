@@ -28,7 +28,9 @@ thread_local std::string g_err;
 thread_local bsg_timings g_tm;
 
 constexpr int kSlots = 4;                       // staging ring depth
-constexpr int64_t kDefaultBatch = 64ll << 20;   // uncompressed bytes per batch
+constexpr int64_t kDefaultBatch = 64ll << 20;   // uncompressed bytes per batch (host inflate)
+constexpr int64_t kDefaultGpuBatch = 256ll << 20;   // uncompressed bytes per batch (GPU inflate)
+constexpr size_t kCompChunk = 16u << 20;        // compressed bytes per pinned upload chunk (GPU inflate)
 constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
@@ -72,6 +74,9 @@ struct DeviceCtx {
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
     DevBuf tab[5], c0, c1, tiles_i32, tiles_i64, out, scalars;
     DevBuf raw_all, offs_all, batch_table;      // resident raw bytes of a staged session
+    DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
+    PinBuf h_total;
+    cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {};
     PinBuf h_scalars, h_out[2], h_tiles;
     cudaEvent_t ev_d2h[2] = {};
     std::vector<cudaEvent_t> ev_pool;
@@ -87,7 +92,14 @@ struct DeviceCtx {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
         }
-        for (int i = 0; i < 2; ++i) BSG_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_total[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_gfree[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < kSlots; ++i) BSG_CUDA(cudaEventCreateWithFlags(&ev_pin[i], cudaEventDisableTiming));
+        h_total.ensure(64);
+        g_total.ensure(64);
         h_scalars.ensure(sizeof(DeviceScalars));
         init = true;
     }
@@ -112,6 +124,12 @@ struct DeviceCtx {
         raw_all.release(); offs_all.release(); batch_table.release(); h_scalars.release();
         h_out[0].release(); h_out[1].release(); h_tiles.release();
         cudaEventDestroy(ev_d2h[0]); cudaEventDestroy(ev_d2h[1]);
+        for (int i = 0; i < 2; ++i) {
+            g_comp[i].release(); g_raw[i].release(); g_offs[i].release(); g_blocks[i].release(); g_walkers[i].release();
+            g_counts[i].release(); g_base[i].release(); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_gfree[i]);
+        }
+        for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev_pin[i]);
+        g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
         cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp);
@@ -191,6 +209,7 @@ public:
         : bamp_(open_bam(bampath)), bam_(*bamp_) {
         if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) opts_ = *opts;
         else { memset(&opts_, 0, sizeof opts_); opts_.verify_crc = 1; }
+        if (const char* e = getenv("BSG_GPU_INFLATE")) opts_.gpu_inflate = atoi(e);   // experiment switch
         resolve_regions(bam_, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg_);
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -212,7 +231,8 @@ public:
         keep_raw_ = keep_raw;
         segs_.clear();
         plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
-        const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : kDefaultBatch;
+        const bool gpu = opts_.gpu_inflate != 0;
+        const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : (gpu ? kDefaultGpuBatch : kDefaultBatch);
         // group segments into batches
         batches_.clear();
         uint64_t max_batch = 0, total_bytes = 0, total_c = 0;
@@ -249,6 +269,22 @@ public:
         const size_t max_offs = size_t(max_batch / kMinRecord) + 1;
         size_t max_segs = 0;
         for (auto& b : batches_) max_segs = std::max(max_segs, b->seg_last - b->seg_first);
+        if (keep_raw) {
+            size_t tot = 0;
+            for (auto& b : batches_) tot += (b->bytes + 64 + 255) & ~255ull;
+            c.raw_all.ensure(tot + 64);
+            size_t offs_tot = size_t(rows_cap_) + batches_.size() + 8;
+            if (gpu) { offs_tot = 8; for (auto& b : batches_) offs_tot += size_t(b->bytes / kMinRecord) + 2; }
+            c.offs_all.ensure(offs_tot * sizeof(uint32_t));
+        }
+        ensure_table(rows_cap_);
+        c.scalars.ensure(sizeof(DeviceScalars));
+        BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
+        if (gpu) {
+            run_pipeline_gpu(max_batch, max_offs);
+            tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
+            return;
+        }
         for (int s = 0; s < kSlots && s < int(batches_.size()); ++s) {
             c.h_raw[s].ensure(max_batch + 64);
             c.h_offs[s].ensure((max_offs + max_segs + 8) * sizeof(uint32_t));
@@ -257,16 +293,6 @@ public:
                 c.d_offs[s].ensure((max_offs + 8) * sizeof(uint32_t));
             }
         }
-        if (keep_raw) {
-            size_t tot = 0;
-            for (auto& b : batches_) tot += (b->bytes + 64 + 255) & ~255ull;
-            c.raw_all.ensure(tot + 64);
-            c.offs_all.ensure((size_t(rows_cap_) + batches_.size() + 8) * sizeof(uint32_t));
-        }
-        ensure_table(rows_cap_);
-        c.scalars.ensure(sizeof(DeviceScalars));
-        BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
-
         run_pipeline();
         tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
     }
@@ -397,11 +423,16 @@ public:
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         tm_.ms_d2h = now_ms() - t_d2h;
         const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
-        if (hs->status & STATUS_CORRUPT) fail(BSG_EFORMAT, "corrupt BAM record (CIGAR beyond record end) in " + bam_.path());
-        if (hs->status & STATUS_UNSORTED) fail(BSG_EUNSORTED, "BAM file is not coordinate-sorted: " + bam_.path());
+        check_status(hs->status);
         tm_.records = n_rows_;
         tm_.records_kept = int64_t(hs->kept);
         tm_.candidates = int64_t(hs->candidates);
+    }
+
+    void check_status(uint32_t status) {
+        if (status & STATUS_BAD_DEFLATE) fail(BSG_EFORMAT, "BGZF inflate failed (corrupt DEFLATE stream or ISIZE mismatch) in " + bam_.path());
+        if (status & STATUS_CORRUPT) fail(BSG_EFORMAT, "corrupt BAM record chain in " + bam_.path());
+        if (status & STATUS_UNSORTED) fail(BSG_EUNSORTED, "BAM file is not coordinate-sorted: " + bam_.path());
     }
 
     void finish_timings(double t_start) {
@@ -587,25 +618,183 @@ private:
             throw;
         }
         BSG_CUDA(cudaStreamSynchronize(c.s_copy));
-        if (keep_raw_) {
-            std::vector<DecodeBatch> tab;
-            int chunks = 0;
-            int64_t row0 = 0;
-            for (auto& rb : resident_) {
-                if (rb.n > 0) {
-                    tab.push_back(DecodeBatch{c.raw_all.as<uint8_t>() + rb.raw_base, c.offs_all.as<uint32_t>() + rb.offs_base, row0, int32_t(rb.n), chunks});
-                    chunks += int((rb.n + kDecodeChunk - 1) / kDecodeChunk);
-                }
-                row0 += rb.n;
-            }
-            resident_.resize(tab.size());
-            resident_chunks_ = chunks;
-            c.batch_table.ensure(tab.size() * sizeof(DecodeBatch) + 64);
-            if (!tab.empty()) BSG_CUDA(cudaMemcpy(c.batch_table.p, tab.data(), tab.size() * sizeof(DecodeBatch), cudaMemcpyHostToDevice));
-            BSG_CUDA(cudaStreamSynchronize(c.s_comp));
-        }
+        if (keep_raw_) build_resident_table();
         tm_.ms_h2d = h2d_ms;
         tm_.records = n_rows_;
+    }
+
+    // GPU-inflate pipeline: host ships compressed bytes; inflate, record walk and decode run on the device.
+    // Batch b: [host: descriptors + memcpy file -> pinned chunks -> H2D] -> inflate -> walk (count/scan/write) ->
+    // total read-back; K1 for batch b is launched one iteration later so that the host work of batch b+1 overlaps the
+    // device work of batch b.
+    void run_pipeline_gpu(uint64_t max_batch, size_t max_offs) {
+        DeviceCtx& c = *ctx_;
+        const size_t nb = batches_.size();
+        resident_.clear();
+        n_rows_ = 0;
+        const std::vector<uint64_t>& ent = bam_.entry_points();
+        uint64_t raw_base = 0; int64_t offs_base = 0;
+        struct Pending { bool valid = false; int slot = 0; uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0; };
+        Pending pend;
+        std::vector<Span> inflate_spans;
+        auto finish = [&](Pending& p) {
+            if (!p.valid) return;
+            BSG_CUDA(cudaEventSynchronize(c.ev_total[p.slot]));
+            const int64_t n = int64_t(c.h_total.as<uint32_t>()[p.slot]);
+            if (n_rows_ + n > rows_cap_) fail(BSG_EFORMAT, "record count exceeds the planned table capacity");
+            if (keep_raw_) {
+                resident_.push_back(ResidentBatch{p.raw_base, p.offs_base, n});
+            } else {
+                Span sp{c.timing_event(), c.timing_event()};
+                BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_comp);
+                BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+                kt_.decode.push_back(sp); kt_.launches += n > 0;
+            }
+            BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], c.s_comp));
+            n_rows_ += n;
+            p.valid = false;
+        };
+        std::vector<InflateBlock> blocks;
+        std::vector<uint2> walkers;
+        struct CopyPiece { uint64_t file_off, dst_off, len; };
+        std::vector<CopyPiece> pieces;
+        int pin_slot = 0;
+        for (size_t bi = 0; bi < nb; ++bi) {
+            Batch* b = batches_[bi].get();
+            const int slot = int(bi & 1);
+            // ---- descriptors -----------------------------------------------------------------------------------------
+            blocks.clear(); walkers.clear(); pieces.clear();
+            uint64_t ubase = 0, cbase = 0;
+            for (size_t k = b->seg_first; k < b->seg_last; ++k) {
+                const Segment& sg = segs_[k];
+                if (sg.blocks.empty()) continue;
+                const uint64_t fbeg = sg.blocks.front().coff, fend = sg.blocks.back().coff + sg.blocks.back().csize;
+                pieces.push_back(CopyPiece{fbeg, cbase, fend - fbeg});
+                uint64_t u = ubase;
+                // walkers: the segment start plus every index entry point strictly inside the segment
+                auto it = std::upper_bound(ent.begin(), ent.end(), sg.vbeg);
+                uint32_t prev = uint32_t(ubase + sg.ubeg);
+                const uint32_t seg_end = uint32_t(ubase + sg.uend);
+                for (const BlockInfo& blk : sg.blocks) {
+                    while (it != ent.end() && (*it >> 16) < blk.coff) ++it;      // stale entries cost parallelism, not correctness
+                    blocks.push_back(InflateBlock{uint32_t(cbase + (blk.coff - fbeg) + blk.hdr), blk.csize - blk.hdr - 8, uint32_t(u), blk.isize});
+                    for (; it != ent.end() && *it < sg.vend && (*it >> 16) == blk.coff; ++it) {
+                        const uint64_t uo = *it & 0xffff;
+                        if (uo > blk.isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam_.path());
+                        const uint32_t pos = uint32_t(u + uo);
+                        if (pos > prev && pos < seg_end) { walkers.push_back(make_uint2(prev, pos)); prev = pos; }
+                    }
+                    u += blk.isize;
+                }
+                if (seg_end > prev) walkers.push_back(make_uint2(prev, seg_end));
+                ubase += (sg.usize + 15) & ~15ull;
+                cbase += (fend - fbeg + 15) & ~15ull;
+            }
+            const uint32_t end_pos = walkers.empty() ? 0u : walkers.back().y;
+            // ---- buffers ------------------------------------------------------------------------------------------------
+            BSG_CUDA(cudaEventSynchronize(c.ev_gfree[slot]));          // K1 of the batch that used this slot is done
+            c.g_comp[slot].ensure(cbase + 64);
+            c.g_blocks[slot].ensure(blocks.size() * sizeof(InflateBlock) + 64);
+            c.g_walkers[slot].ensure(walkers.size() * sizeof(uint2) + 64);
+            c.g_counts[slot].ensure(walkers.size() * 4 + 64);
+            c.g_base[slot].ensure(walkers.size() * 4 + 64);
+            uint8_t* d_raw; uint32_t* d_offs;
+            if (keep_raw_) {
+                d_raw = c.raw_all.as<uint8_t>() + raw_base;
+                d_offs = c.offs_all.as<uint32_t>() + offs_base;
+            } else {
+                c.g_raw[slot].ensure(max_batch + 64);
+                c.g_offs[slot].ensure((max_offs + 8) * sizeof(uint32_t));
+                d_raw = c.g_raw[slot].as<uint8_t>();
+                d_offs = c.g_offs[slot].as<uint32_t>();
+            }
+            // ---- compressed bytes: file (page cache) -> pinned chunk -> device, chunk by chunk ----------------------------
+            {
+                // flatten the pieces into kCompChunk-sized uploads
+                size_t pi = 0; uint64_t done_in_piece = 0;
+                while (pi < pieces.size()) {
+                    const int ps = pin_slot; pin_slot = (pin_slot + 1) % kSlots;
+                    c.h_raw[ps].ensure(kCompChunk + 64);
+                    BSG_CUDA(cudaEventSynchronize(c.ev_pin[ps]));
+                    uint8_t* pin = c.h_raw[ps].as<uint8_t>();
+                    // gather as many (partial) pieces as fit
+                    struct Part { const uint8_t* src; uint64_t pin_off, dst_off, len; };
+                    std::vector<Part> parts;
+                    uint64_t fill = 0;
+                    while (pi < pieces.size() && fill < kCompChunk) {
+                        const CopyPiece& pc = pieces[pi];
+                        const uint64_t take = std::min<uint64_t>(pc.len - done_in_piece, kCompChunk - fill);
+                        parts.push_back(Part{bam_.data() + pc.file_off + done_in_piece, fill, pc.dst_off + done_in_piece, take});
+                        fill += take; done_in_piece += take;
+                        if (done_in_piece == pc.len) { ++pi; done_in_piece = 0; }
+                    }
+                    // parallel memcpy into the pinned chunk (1 MiB tasks)
+                    std::vector<Part> tasks;
+                    for (const Part& pt : parts)
+                        for (uint64_t o = 0; o < pt.len; o += (1u << 20))
+                            tasks.push_back(Part{pt.src + o, pt.pin_off + o, 0, std::min<uint64_t>(1u << 20, pt.len - o)});
+                    pool_->parallel_for(int64_t(tasks.size()), 1, [&](int64_t a, int64_t e, int) {
+                        for (int64_t t = a; t < e; ++t) memcpy(pin + tasks[t].pin_off, tasks[t].src, tasks[t].len);
+                    });
+                    for (const Part& pt : parts)
+                        BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + pt.dst_off, pin + pt.pin_off, pt.len, cudaMemcpyHostToDevice, c.s_copy));
+                    BSG_CUDA(cudaEventRecord(c.ev_pin[ps], c.s_copy));
+                }
+            }
+            if (!blocks.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_blocks[slot].p, blocks.data(), blocks.size() * sizeof(InflateBlock), cudaMemcpyHostToDevice, c.s_copy));
+            if (!walkers.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, walkers.data(), walkers.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.s_copy));
+            BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
+            BSG_CUDA(cudaStreamSynchronize(c.s_copy));                 // blocks/walkers vectors are reused next iteration
+            // ---- device: inflate -> walk -> total ------------------------------------------------------------------------------
+            BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            launch_inflate(c.g_blocks[slot].as<InflateBlock>(), int(blocks.size()), c.g_comp[slot].as<uint8_t>(), d_raw,
+                           c.scalars.as<DeviceScalars>(), c.s_comp);
+            launch_walk(d_raw, c.g_walkers[slot].as<uint2>(), int(walkers.size()), c.g_counts[slot].as<uint32_t>(),
+                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, d_offs, end_pos,
+                        c.scalars.as<DeviceScalars>(), c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            inflate_spans.push_back(sp);
+            kt_.launches += (blocks.empty() ? 0 : 1) + (walkers.empty() ? 1 : 3);
+            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, c.s_comp));
+            BSG_CUDA(cudaEventRecord(c.ev_total[slot], c.s_comp));
+            // ---- previous batch: decode ------------------------------------------------------------------------------------------
+            finish(pend);
+            pend.valid = true; pend.slot = slot; pend.d_raw = d_raw; pend.d_offs = d_offs; pend.raw_base = raw_base; pend.offs_base = offs_base;
+            if (keep_raw_) {
+                raw_base += (b->bytes + 64 + 255) & ~255ull;
+                offs_base += int64_t((b->bytes) / kMinRecord) + 2;
+            }
+        }
+        finish(pend);
+        BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        tm_.ms_inflate_gpu = sum_ms(inflate_spans);
+        BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, c.scalars.p, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
+        BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        check_status(c.h_scalars.as<DeviceScalars>()->status);
+        if (keep_raw_) build_resident_table();
+        tm_.records = n_rows_;
+    }
+
+    void build_resident_table() {
+        DeviceCtx& c = *ctx_;
+        std::vector<DecodeBatch> tab;
+        int chunks = 0;
+        int64_t row0 = 0;
+        for (auto& rb : resident_) {
+            if (rb.n > 0) {
+                tab.push_back(DecodeBatch{c.raw_all.as<uint8_t>() + rb.raw_base, c.offs_all.as<uint32_t>() + rb.offs_base, row0, int32_t(rb.n), chunks});
+                chunks += int((rb.n + kDecodeChunk - 1) / kDecodeChunk);
+            }
+            row0 += rb.n;
+        }
+        resident_.resize(tab.size());
+        resident_chunks_ = chunks;
+        c.batch_table.ensure(tab.size() * sizeof(DecodeBatch) + 64);
+        if (!tab.empty()) BSG_CUDA(cudaMemcpy(c.batch_table.p, tab.data(), tab.size() * sizeof(DecodeBatch), cudaMemcpyHostToDevice));
+        BSG_CUDA(cudaStreamSynchronize(c.s_comp));
     }
 
     struct ResidentBatch { uint64_t raw_base; int64_t offs_base; int64_t n; };

@@ -51,7 +51,7 @@ struct DeviceScalars {
     unsigned long long kept;
     unsigned long long candidates;
 };
-enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u };
+enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u, STATUS_BAD_DEFLATE = 4u };
 
 constexpr int kTileInts = 8192;   // int32 per counting tile (32 KiB of shared memory)
 
@@ -71,6 +71,20 @@ constexpr int kDecodeChunk = 256;
 void launch_decode(const DecodeBatch& one, ReadTable t, DeviceScalars* sc, cudaStream_t s);
 void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, DeviceScalars* sc,
                          cudaStream_t s);
+
+// K0 (gpu_inflate): one BGZF block = one raw-DEFLATE stream of at most 64 KiB.
+struct InflateBlock {
+    uint32_t in_off;    // byte offset of the DEFLATE payload in the batch's compressed buffer
+    uint32_t in_len;    // payload bytes (block size - header - 8)
+    uint32_t out_off;   // byte offset in the batch's raw buffer
+    uint32_t out_len;   // ISIZE
+};
+void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
+                    cudaStream_t s);
+// Record-boundary walk from index entry points: walkers[w] = (begin, end) byte positions in d_raw.  Two passes
+// (count, scan, write) fill d_offs[0..total] (+ end sentinel) and *d_total.
+void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
+                 uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
 
 // K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415).
 void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);

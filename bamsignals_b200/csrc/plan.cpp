@@ -105,7 +105,9 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     for (size_t i = 0; i < qs.size();) {
         Q cur = qs[i];
         size_t j = i + 1;
-        for (; j < qs.size() && qs[j].rid == cur.rid && qs[j].beg <= cur.end + 16384; ++j) cur.end = std::max(cur.end, qs[j].end);
+        // queries closer than the genomic span of one BGZF block would fetch the same blocks: ask the index once
+        const int64_t gap = bam.bp_per_block(cur.rid);
+        for (; j < qs.size() && qs[j].rid == cur.rid && qs[j].beg <= cur.end + gap; ++j) cur.end = std::max(cur.end, qs[j].end);
         bam.query(cur.rid, cur.beg, cur.end, &ranges);
         i = j;
     }

@@ -108,7 +108,7 @@ def run_ours(args, rank, world, local_rank):
     gr_all, kw, fn = WL.regions(preset, gs)
     gr, _ = WL.shard_regions(gr_all, rank, world)
     ca = B.core_args(fn, **kw)
-    opts = B.default_opts(devices=[local_rank])
+    opts = B.default_opts(devices=[local_rank], inflate_threads=max(1, (os.cpu_count() or 1) // world))
     is_cov = fn == "bamCoverage"
     ext = (ca["tlen_filter"][1] if (is_cov and ca["tspan"]) else 0) if is_cov else \
         abs(ca["shift"]) + (ca["tlen_filter"][1] if ca["pe_mid"] else 0)

@@ -157,3 +157,73 @@ def test_properties_at_scale(gen_dir):
     c2 = B.bamCoverage(bam, flipped).alignSignals()
     assert np.array_equal(c1, c2[::-1])
     assert B.timings()["records"] > 0.3 * info["records"]
+
+
+# ---- GPU-side inflate + record walk (opts.gpu_inflate = 1): same results, bit for bit ---------------------------------
+GPUI = dict(gpu_inflate=1)
+
+
+@pytest.mark.parametrize("preset,gs,record", [("c2", 0.002, "compact"), ("c2", 0.001, "realistic"), ("c3", 0.004, "compact"),
+                                              ("c4", 0.002, "compact"), ("c5", 0.002, "compact")])
+def test_gpu_inflate_scaled_configs(gen_dir, preset, gs, record):
+    bam, info = WL.make_bam(preset, gs, gen_dir, record=record, unplaced=7)
+    gr, kw, fn = WL.regions(preset, gs)
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(**GPUI), **kw)
+    t = B.timings()
+    want = getattr(O, fn)(bam, gr, nthreads=8, **kw)
+    assert np.array_equal(WL.as_flat(got), WL.as_flat(want))
+    assert t["ms_inflate_gpu"] > 0 and t["records"] > 0
+
+
+@pytest.mark.parametrize("batch_bytes", [1 << 16, 1 << 20, 0])
+def test_gpu_inflate_batching(gen_dir, batch_bytes):
+    bam, _ = WL.make_bam("c4", 0.002, gen_dir, unplaced=7)
+    gr, kw, fn = WL.regions("c4", 0.002)
+    ref = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch_bytes, **GPUI), **kw)
+    assert np.array_equal(WL.as_flat(got), ref)
+
+
+def test_gpu_inflate_reference_fixture(fixture_bam):
+    """The reference's own BAM (written by htslib, deflate level 6) through the GPU inflate path."""
+    import spec_r
+    genes = spec_r.test_regions()
+    gr = B.GRanges([["chr1", "chr2", "chr3"][i] for i in genes["rname"]], genes["start"], genes["width"], genes["strand"])
+    o = B.default_opts(**GPUI)
+    for case in list(spec_r.sweep_pileup())[::5]:
+        kw = dict(mapqual=case["mapqual"], shift=case["shift"], ss=case["ss"], paired_end=case["paired_end"], tlenFilter=case["tlenFilter"])
+        assert np.array_equal(B.bamCount(fixture_bam, gr, opts=o, **kw), O.bamCount(fixture_bam, gr, **kw))
+        same(B.bamProfile(fixture_bam, gr, opts=o, **kw).as_list(), O.bamProfile(fixture_bam, gr, **kw).as_list())
+    same(B.bamCoverage(fixture_bam, gr, opts=o, paired_end="extend").as_list(), O.bamCoverage(fixture_bam, gr, paired_end="extend").as_list())
+    wide = B.GRanges(["chr1", "chr2", "chr3"], [1, 1, 1], [10237, 10279, 10238], ["+", "-", "*"])
+    same(B.bamCoverage(fixture_bam, wide, opts=o).as_list(), O.bamCoverage(fixture_bam, wide).as_list())
+
+
+@pytest.mark.parametrize("level,straddle,payload", [(0, False, 3000), (1, True, 997), (6, False, 0xFF00), (9, True, 20000), (6, False, 40)])
+def test_gpu_inflate_deflate_variants(tmp_path, level, straddle, payload):
+    """Stored blocks (level 0), fixed-Huffman blocks (tiny payloads), dynamic blocks at several levels, straddling records."""
+    p = str(tmp_path / "v.bam")
+    reads = E.variety_reads(n=1500)
+    W.write_bam(p, E.REFS, reads, block_payload=payload, cut_mid_record=straddle, level=level)
+    gr = E.variety_regions()
+    o = B.default_opts(**GPUI)
+    assert np.array_equal(B.bamCount(p, gr, ss=True, shift=33, opts=o), O.bamCount(p, gr, ss=True, shift=33))
+    same(B.bamCoverage(p, gr, opts=o).as_list(), O.bamCoverage(p, gr).as_list())
+
+
+def test_gpu_inflate_corrupt_stream(tmp_path, fixture_bam):
+    raw = bytearray(open(fixture_bam, "rb").read())
+    raw[200000] ^= 0xFF
+    p = str(tmp_path / "corrupt.bam")
+    open(p, "wb").write(raw)
+    open(p + ".bai", "wb").write(open(fixture_bam + ".bai", "rb").read())
+    gr = B.GRanges(["chr1", "chr2", "chr3"], [1, 1, 1], [10000] * 3)
+    try:
+        got = B.bamCount(p, gr, opts=B.default_opts(**GPUI))
+    except B.BamsignalsError as e:
+        assert e.code in (-4, -5)
+    else:
+        # a flipped bit inside a literal changes data but not the stream structure: CRC32 is not checked on the
+        # GPU path yet (DESIGN.md), so the call may succeed; it must at least not crash
+        assert got.shape == (3,)
+    assert np.array_equal(B.bamCount(fixture_bam, gr, opts=B.default_opts(**GPUI)), O.bamCount(fixture_bam, gr))

@@ -94,32 +94,48 @@ class CountSignals:
     """List-like container: signal i is a (w,) int32 vector, or a (2, w) matrix [sense; antisense] when ss.
 
     The (2, w) matrices are Fortran-ordered views into the flat result buffer, i.e. the memory layout of R's
-    IntegerMatrix(2, w) (src/bamsignals.cpp:178-181): [sense_0, antisense_0, sense_1, ...]."""
+    IntegerMatrix(2, w) (src/bamsignals.cpp:178-181): [sense_0, antisense_0, sense_1, ...].  When built from the
+    library's flat result (`flat` + `offsets`) the per-region views are created on first use."""
 
     rownames = ("sense", "antisense")
 
-    def __init__(self, signals: List[np.ndarray], ss: bool):
-        self.signals = signals
+    def __init__(self, signals: Optional[List[np.ndarray]], ss: bool, flat: Optional[np.ndarray] = None,
+                 offsets: Optional[np.ndarray] = None):
         self.ss = bool(ss)
-        for s in signals:                                    # checkList, src/CountSignals.cpp:4-16
-            if self.ss and not (s.ndim == 2 and s.shape[0] == 2):
-                raise ValueError("strand-specific signals must be matrices with two rows")
-            if not self.ss and s.ndim != 1:
-                raise ValueError("signals must be vectors")
+        self._signals = signals
+        self._flat, self._offsets = flat, offsets
+        if signals is not None:
+            for s in signals:                                # checkList, src/CountSignals.cpp:4-16
+                if self.ss and not (s.ndim == 2 and s.shape[0] == 2):
+                    raise ValueError("strand-specific signals must be matrices with two rows")
+                if not self.ss and s.ndim != 1:
+                    raise ValueError("signals must be vectors")
+
+    def _view(self, i):
+        v = self._flat[self._offsets[i]:self._offsets[i + 1]]
+        return v.reshape((2, -1), order="F") if self.ss else v
+
+    @property
+    def signals(self):
+        if self._signals is None:
+            self._signals = [self._view(i) for i in range(len(self._offsets) - 1)]
+        return self._signals
 
     def __len__(self):                                       # R/zzzCountSignals.R:46
-        return len(self.signals)
+        return len(self._signals) if self._signals is not None else len(self._offsets) - 1
 
     def width(self):                                         # R/zzzCountSignals.R:54-56 (fastWidth)
-        return np.array([s.shape[-1] for s in self.signals], dtype=np.int64)
+        if self._signals is None:
+            return np.diff(self._offsets) // (2 if self.ss else 1)
+        return np.array([s.shape[-1] for s in self._signals], dtype=np.int64)
 
     def __getitem__(self, i):                                # R/zzzCountSignals.R:68-77
         if isinstance(i, (int, np.integer)):
-            if i < 0 or i >= len(self.signals):
+            if i < 0 or i >= len(self):
                 raise IndexError("subscript out of bounds")
-            return self.signals[i]
-        idx = np.arange(len(self.signals))[i]
-        return CountSignals([self.signals[k] for k in idx], self.ss)
+            return self._signals[i] if self._signals is not None else self._view(int(i))
+        idx = np.arange(len(self))[i]
+        return CountSignals([self[int(k)] for k in idx], self.ss)
 
     def as_list(self):                                       # R/zzzCountSignals.R:83-96
         return list(self.signals)
@@ -128,9 +144,12 @@ class CountSignals:
         w = self.width()
         if len(w) and (w != w[0]).any():
             raise ValueError("all signals must have the same width")
-        if not self.signals:
+        if len(self) == 0:
             return np.zeros((0,), dtype=np.int32)
-        return np.stack(self.signals, axis=-1)               # [w, R] or [2, w, R] like simplify2array
+        if self._signals is None:                            # contiguous result: one reshape, no copies
+            a = self._flat.reshape((len(self), -1))
+            return a.T if not self.ss else a.reshape((len(self), -1, 2)).transpose(2, 1, 0)
+        return np.stack(self._signals, axis=-1)              # [w, R] or [2, w, R] like simplify2array
 
     def __repr__(self):
         kind = "strand-specific" if self.ss else "strand-unspecific"
@@ -280,7 +299,7 @@ def timings() -> dict:
 
 
 def pileup_core(bampath, gr, tlen_filter, mapqual=0, binsize=1, shift=0, ss=False, requiredF=0, filteredF=-1,
-                pe_mid=False, maxgap=16385, opts: Optional[BsgOpts] = None):
+                pe_mid=False, maxgap=16385, opts: Optional[BsgOpts] = None, _lazy=False):
     """The .Call('bamsignals_pileup_core') entry point (src/bamsignals.cpp:444-461); binsize <= 0 means bamCount.
     Returns the R `List`: one flat vector / (2,R) matrix for bamCount, else one array per region."""
     m = marshal_regions(gr)
@@ -296,11 +315,13 @@ def pileup_core(bampath, gr, tlen_filter, mapqual=0, binsize=1, shift=0, ss=Fals
     _check(rc)
     if binsize <= 0:
         return [flat.reshape((2, -1), order="F") if ss else flat]
+    if _lazy:
+        return flat, off
     return split_signals(flat, off, bool(ss))
 
 
 def coverage_core(bampath, gr, tlen_filter, mapqual=0, requiredF=0, filteredF=-1, tspan=False, maxgap=16385,
-                  opts: Optional[BsgOpts] = None):
+                  opts: Optional[BsgOpts] = None, _lazy=False):
     """The .Call('bamsignals_coverage_core') entry point (src/bamsignals.cpp:474-494)."""
     m = marshal_regions(gr)
     off = output_layout(m.width, 1, False)
@@ -312,6 +333,8 @@ def coverage_core(bampath, gr, tlen_filter, mapqual=0, requiredF=0, filteredF=-1
                             int(bool(tspan)), int(maxgap), _p(flat, C.c_int32), _p(off, C.c_int64), None,
                             None if opts is None else C.byref(opts))
     _check(rc)
+    if _lazy:
+        return flat, off
     return split_signals(flat, off, False)
 
 
@@ -411,15 +434,15 @@ def bamProfile(bampath, gr, binsize=1, mapqual=0, shift=0, ss=False, paired_end=
                       "some bins will correspond to less than binsize basepairs")     # R/wrappers.R:138-141
     pe = _match_arg(paired_end, ("ignore", "filter", "midpoint"))
     bampath = os.path.expanduser(bampath)
-    pu = pileup_core(bampath, gr, _tlen(tlenFilter, pe), _trunc(mapqual), _trunc(binsize), _trunc(shift), ss,
-                     flagMask(pe), _trunc(filteredFlag), pe == "midpoint", opts=opts)
-    return CountSignals(pu, ss)
+    flat, off = pileup_core(bampath, gr, _tlen(tlenFilter, pe), _trunc(mapqual), _trunc(binsize), _trunc(shift), ss,
+                            flagMask(pe), _trunc(filteredFlag), pe == "midpoint", opts=opts, _lazy=True)
+    return CountSignals(None, ss, flat=flat, offsets=off)
 
 
 def bamCoverage(bampath, gr, mapqual=0, paired_end=("ignore", "extend"), tlenFilter=None, filteredFlag=-1,
                 verbose=False, opts=None):
     pe = _match_arg(paired_end, ("ignore", "extend"))
     bampath = os.path.expanduser(bampath)
-    pu = coverage_core(bampath, gr, _tlen(tlenFilter, pe), _trunc(mapqual), flagMask(pe), _trunc(filteredFlag),
-                       pe == "extend", opts=opts)
-    return CountSignals(pu, False)
+    flat, off = coverage_core(bampath, gr, _tlen(tlenFilter, pe), _trunc(mapqual), flagMask(pe), _trunc(filteredFlag),
+                              pe == "extend", opts=opts, _lazy=True)
+    return CountSignals(None, False, flat=flat, offsets=off)

@@ -29,7 +29,7 @@ thread_local bsg_timings g_tm;
 
 constexpr int kSlots = 4;                       // staging ring depth
 constexpr int64_t kDefaultBatch = 64ll << 20;   // uncompressed bytes per batch (host inflate)
-constexpr int64_t kDefaultGpuBatch = 256ll << 20;   // uncompressed bytes per batch (GPU inflate)
+constexpr int64_t kDefaultGpuBatch = 1024ll << 20;   // uncompressed bytes per batch (GPU inflate)
 constexpr size_t kCompChunk = 16u << 20;        // compressed bytes per pinned upload chunk (GPU inflate)
 constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
@@ -209,7 +209,8 @@ public:
         : bamp_(open_bam(bampath)), bam_(*bamp_) {
         if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) opts_ = *opts;
         else { memset(&opts_, 0, sizeof opts_); opts_.verify_crc = 1; }
-        if (const char* e = getenv("BSG_GPU_INFLATE")) opts_.gpu_inflate = atoi(e);   // experiment switch
+        if (const char* e = getenv("BSG_GPU_INFLATE")) opts_.gpu_inflate = atoi(e);   // experiment switches
+        if (const char* e = getenv("BSG_BATCH_MB")) opts_.batch_bytes = int64_t(atoll(e)) << 20;
         resolve_regions(bam_, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg_);
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -320,7 +321,12 @@ public:
             tiles_offsets_.size() == size_t(R + 1) && memcmp(tiles_offsets_.data(), out_offsets, size_t(R + 1) * 8) == 0)
             return;
         HostTiles ht;
-        make_tiles(rg_, mode, binsize, ss, out_offsets, kTileInts, &ht);
+        // Tile size: as large as shared memory allows (fewer halo re-reads), but small enough that the launch has
+        // >= ~16 CTAs per SM: a few huge regions (C4: 24 whole chromosomes) must still fill 148 SMs.
+        const int64_t total_ints = out_offsets[R];
+        int tile_ints = kTileInts;
+        while (tile_ints > 512 && total_ints / tile_ints < 148 * 16) tile_ints >>= 1;
+        make_tiles(rg_, mode, binsize, ss, out_offsets, tile_ints, &ht);
         const int64_t nt = ht.size();
         c.tiles_i32.ensure(size_t(nt) * 4 * sizeof(int32_t) + 64);
         c.tiles_i64.ensure(size_t(nt) * 3 * sizeof(int64_t) + 64);
@@ -636,7 +642,7 @@ private:
         uint64_t raw_base = 0; int64_t offs_base = 0;
         struct Pending { bool valid = false; int slot = 0; uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0; };
         Pending pend;
-        std::vector<Span> inflate_spans;
+        std::vector<Span> inflate_spans, walk_spans;
         auto finish = [&](Pending& p) {
             if (!p.valid) return;
             BSG_CUDA(cudaEventSynchronize(c.ev_total[p.slot]));
@@ -655,6 +661,7 @@ private:
             n_rows_ += n;
             p.valid = false;
         };
+        double t_desc = 0, t_copy = 0, t_wait = 0, t_finish = 0;
         std::vector<InflateBlock> blocks;
         std::vector<uint2> walkers;
         struct CopyPiece { uint64_t file_off, dst_off, len; };
@@ -664,6 +671,7 @@ private:
             Batch* b = batches_[bi].get();
             const int slot = int(bi & 1);
             // ---- descriptors -----------------------------------------------------------------------------------------
+            double tt = now_ms();
             blocks.clear(); walkers.clear(); pieces.clear();
             uint64_t ubase = 0, cbase = 0;
             for (size_t k = b->seg_first; k < b->seg_last; ++k) {
@@ -692,9 +700,11 @@ private:
                 cbase += (fend - fbeg + 15) & ~15ull;
             }
             const uint32_t end_pos = walkers.empty() ? 0u : walkers.back().y;
+            t_desc += now_ms() - tt; tt = now_ms();
             // ---- buffers ------------------------------------------------------------------------------------------------
             BSG_CUDA(cudaEventSynchronize(c.ev_gfree[slot]));          // K1 of the batch that used this slot is done
-            c.g_comp[slot].ensure(cbase + 64);
+            t_wait += now_ms() - tt; tt = now_ms();
+            c.g_comp[slot].ensure(cbase + 4096);   // slack: the bit reader looks ahead, and a corrupt stream may run on for one round
             c.g_blocks[slot].ensure(blocks.size() * sizeof(InflateBlock) + 64);
             c.g_walkers[slot].ensure(walkers.size() * sizeof(uint2) + 64);
             c.g_counts[slot].ensure(walkers.size() * 4 + 64);
@@ -746,12 +756,16 @@ private:
             if (!walkers.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, walkers.data(), walkers.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.s_copy));
             BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
             BSG_CUDA(cudaStreamSynchronize(c.s_copy));                 // blocks/walkers vectors are reused next iteration
+            t_copy += now_ms() - tt; tt = now_ms();
             // ---- device: inflate -> walk -> total ------------------------------------------------------------------------------
             BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
             Span sp{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
             launch_inflate(c.g_blocks[slot].as<InflateBlock>(), int(blocks.size()), c.g_comp[slot].as<uint8_t>(), d_raw,
                            c.scalars.as<DeviceScalars>(), c.s_comp);
+            Span spw{c.timing_event(), sp.b};
+            BSG_CUDA(cudaEventRecord(spw.a, c.s_comp));
+            walk_spans.push_back(spw);
             launch_walk(d_raw, c.g_walkers[slot].as<uint2>(), int(walkers.size()), c.g_counts[slot].as<uint32_t>(),
                         c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, d_offs, end_pos,
                         c.scalars.as<DeviceScalars>(), c.s_comp);
@@ -761,7 +775,9 @@ private:
             BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, c.s_comp));
             BSG_CUDA(cudaEventRecord(c.ev_total[slot], c.s_comp));
             // ---- previous batch: decode ------------------------------------------------------------------------------------------
+            tt = now_ms();
             finish(pend);
+            t_finish += now_ms() - tt;
             pend.valid = true; pend.slot = slot; pend.d_raw = d_raw; pend.d_offs = d_offs; pend.raw_base = raw_base; pend.offs_base = offs_base;
             if (keep_raw_) {
                 raw_base += (b->bytes + 64 + 255) & ~255ull;
@@ -771,6 +787,10 @@ private:
         finish(pend);
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
+        tm_.ms_h2d = t_copy;
+        if (getenv("BSG_DEBUG"))
+            fprintf(stderr, "[bsg] gpu pipeline host ms: descriptors %.1f, slot wait %.1f, memcpy+h2d %.1f, finish(wait total) %.1f; device inflate+walk %.1f (walk %.1f)\n",
+                    t_desc, t_wait, t_copy, t_finish, tm_.ms_inflate_gpu, sum_ms(walk_spans));
         BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, c.scalars.p, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         check_status(c.h_scalars.as<DeviceScalars>()->status);

@@ -1,0 +1,115 @@
+// Host-side unit harness for the GPU inflate kernel's decode core (bamsignals_b200/csrc/inflate_core.cuh): the
+// single-lane part (bit reader, tables, symbols -> token queue) is compiled as-is with g++; the warp-cooperative
+// materialisation (phase 2 of k_inflate_q2) is emulated lane by lane with SIMT load-then-store semantics.
+// Every BGZF block of the given file must reproduce its CRC32 and ISIZE.   usage: harness file.bam
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <zlib.h>
+
+#include "../bamsignals_b200/csrc/inflate_core.cuh"
+
+using namespace bsg::inflate_core;
+
+static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+    static Tables T;
+    static uint32_t q[kQueue];
+    BitReader br;
+    br.init(in);
+    uint32_t op_dec = 0, pos_base = 0;
+    int phase = 0, last = 0, bad = 0;
+    for (;;) {
+        int nq = 0, done = 0;
+        if (phase == 0) {
+            const int h = read_block_header(br, T, &last);
+            if (h == 2) return 2;
+            if (h == 1) {
+                br.consume((32 - br.bo) & 7);
+                const uint32_t v = br.peek();
+                br.consume(32);
+                const uint32_t len = v & 0xffffu, nlen = v >> 16;
+                if ((len ^ nlen) != 0xffffu || op_dec + len > out_len) return 3;
+                const uint8_t* src = br.byte_ptr();
+                memcpy(out + op_dec, src, len);
+                op_dec += len;
+                const uint64_t used = br.bits_used() + uint64_t(len) * 8;
+                (void)used;
+                br.init(src + len);
+                q[0] = kTokSkip | len;
+                nq = 1;
+                if (last) done = 1;
+            } else phase = 1;
+        }
+        if (phase == 1 && nq == 0) {
+            int eob = 0;
+            nq = fill_queue(br, T, q, &op_dec, &eob, &bad);
+            if (eob) { phase = 0; if (last) done = 1; }
+            if (bad || op_dec > out_len) return 4;
+        }
+        // phase 2 emulation
+        for (int base = 0; base < nq; base += 32) {
+            uint32_t t[32], len[32], pos[32];
+            uint32_t run = 0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const bool valid = base + lane < nq;
+                t[lane] = valid ? q[base + lane] : 0;
+                const bool m = valid && (t[lane] >> 31), sk = valid && !m && (t[lane] & kTokSkip);
+                len[lane] = !valid ? 0 : (m ? (t[lane] & 0x1ffu) : (sk ? (t[lane] & 0xffffffu) : 1u));
+                pos[lane] = pos_base + run;
+                run += len[lane];
+                if (valid && !m && !sk) out[pos[lane]] = uint8_t(t[lane]);
+            }
+            for (int k = 0; k < 32; ++k) {
+                if (!(base + k < nq) || !(t[k] >> 31)) continue;
+                const uint32_t mlen = t[k] & 0x1ffu, mdist = ((t[k] >> 16) & 0x7fffu) + 1u, mpos = pos[k];
+                const uint32_t K = mdist >= 32 ? mdist : mdist * (31u / mdist + 1u);
+                for (uint32_t s0 = 0; s0 < mlen; s0 += 32) {
+                    uint8_t tmp[32];
+                    for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) {     // all loads of the step ...
+                        const uint32_t j = s0 + lane;
+                        if (s0 == 0) tmp[lane] = (mdist >= 32 || mdist >= mlen) ? out[mpos + j - mdist] : out[mpos - mdist + (j % mdist)];
+                        else tmp[lane] = out[mpos + j - K];
+                    }
+                    for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) out[mpos + s0 + lane] = tmp[lane];   // ... then all stores
+                }
+            }
+            pos_base += run;
+        }
+        if (done) break;
+    }
+    if (op_dec != out_len || pos_base != out_len) return 5;
+    if (br.bits_used() > uint64_t(in_len) * 8) return 6;
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 2;
+    std::vector<uint8_t> d;
+    uint8_t tmp[65536];
+    size_t k;
+    while ((k = fread(tmp, 1, sizeof tmp, f)) > 0) d.insert(d.end(), tmp, tmp + k);
+    fclose(f);
+    const size_t n = d.size();
+    d.resize(n + 64);
+    size_t off = 0;
+    int nb = 0, bad = 0;
+    while (off + 28 <= n) {
+        const uint8_t* h = d.data() + off;
+        const uint32_t xlen = h[10] | h[11] << 8, bs = (h[16] | h[17] << 8) + 1u;
+        uint32_t isize, crc;
+        memcpy(&isize, h + bs - 4, 4);
+        memcpy(&crc, h + bs - 8, 4);
+        std::vector<uint8_t> out(isize + 64);
+        const int rc = inflate_block(h + 12 + xlen, bs - 12 - xlen - 8, out.data(), isize);
+        if (rc || uint32_t(crc32(crc32(0, nullptr, 0), out.data(), isize)) != crc) {
+            if (++bad < 5) fprintf(stderr, "block %d at %zu: rc %d\n", nb, off, rc);
+        }
+        ++nb;
+        off += bs;
+    }
+    printf("blocks %d bad %d\n", nb, bad);
+    return bad != 0;
+}

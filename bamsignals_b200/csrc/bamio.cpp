@@ -199,7 +199,17 @@ void BamFile::load_index() {
             } else {
                 for (auto& c : cs) { entries_.push_back(c.beg); entries_.push_back(c.end); }
             }
-            refs_[r].bins[bin] = std::move(cs);
+            if (bin >= 4681 && bin < 37449 + 1) {
+                // Leaf bins go into a flat per-window array: the file is coordinate-sorted, so the chunks of a run of
+                // consecutive leaf bins lie between the first bin's first chunk and the last bin's last chunk.
+                const size_t w = bin - 4681;
+                if (refs_[r].leaf.size() <= w) refs_[r].leaf.resize(w + 1, VRange{0, 0});
+                VRange lr{~0ull, 0};
+                for (auto& c : cs) { lr.beg = std::min(lr.beg, c.beg); lr.end = std::max(lr.end, c.end); }
+                if (lr.end > lr.beg) refs_[r].leaf[w] = lr;
+            } else {
+                refs_[r].bins[bin] = std::move(cs);
+            }
         }
         need(4);
         int32_t n_intv = rd_i32(d.data() + p);
@@ -242,16 +252,6 @@ bool BamFile::index_unchanged() const {
            uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec) == index_mtime_ns_;
 }
 
-static void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t>& out) {
-    out.clear();
-    if (beg >= end) return;
-    if (end > (1LL << 29)) end = 1LL << 29;
-    --end;
-    out.push_back(0);
-    for (int shift = 26, t = 1; shift >= 14; shift -= 3, t = (t << 3) + 1)
-        for (int64_t k = t + (beg >> shift); k <= t + (end >> shift); ++k) out.push_back(uint32_t(k));
-}
-
 void BamFile::query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out) const {
     if (tid < 0 || tid >= int(refs_.size())) return;
     const RefIndex& ri = refs_[tid];
@@ -274,16 +274,35 @@ void BamFile::query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out)
         if (r.end > r.beg) out->push_back(r);
         return;
     }
-    thread_local std::vector<uint32_t> bins;
-    reg2bins(beg, end, bins);
-    size_t first = out->size();
-    for (uint32_t b : bins) {
-        auto it = ri.bins.find(b);
-        if (it == ri.bins.end()) continue;
-        for (const VRange& c : it->second)
-            if (c.end > min_off) out->push_back(VRange{std::max(c.beg, min_off), c.end});
+    // levels 0-4: hash lookups (at most 1 + 8 + 64 + 512 + 4096/8 bins for a whole chromosome)
+    int64_t e1 = std::min<int64_t>(end, 1LL << 29) - 1;
+    for (int shift = 26, t = 1; shift >= 17; shift -= 3, t = (t << 3) + 1)
+        for (int64_t k = t + (beg >> shift); k <= t + (e1 >> shift); ++k) {
+            auto it = ri.bins.find(uint32_t(k));
+            if (it == ri.bins.end()) continue;
+            for (const VRange& c : it->second)
+                if (c.end > min_off) out->push_back(VRange{std::max(c.beg, min_off), c.end});
+        }
+    {
+        auto it = ri.bins.find(0);
+        if (it != ri.bins.end())
+            for (const VRange& c : it->second)
+                if (c.end > min_off) out->push_back(VRange{std::max(c.beg, min_off), c.end});
     }
-    (void)first;
+    // level 5: one range from the first to the last non-empty window of the query
+    if (!ri.leaf.empty()) {
+        int64_t w0 = beg >> 14, w1 = std::min<int64_t>(e1 >> 14, int64_t(ri.leaf.size()) - 1);
+        while (w0 <= w1 && ri.leaf[size_t(w0)].end == 0) ++w0;
+        while (w1 >= w0 && ri.leaf[size_t(w1)].end == 0) --w1;
+        if (w0 <= w1) {
+            uint64_t lo = ~0ull, hi = 0;
+            // chunk bounds are monotone along a sorted file, but take min/max over the ends to be safe with odd indexers
+            lo = std::min(ri.leaf[size_t(w0)].beg, ri.leaf[size_t(w1)].beg);
+            hi = std::max(ri.leaf[size_t(w0)].end, ri.leaf[size_t(w1)].end);
+            for (int64_t w = w0; w <= w1; ++w) hi = std::max(hi, ri.leaf[size_t(w)].end);
+            if (hi > min_off) out->push_back(VRange{std::max(lo, min_off), hi});
+        }
+    }
 }
 
 }  // namespace bsg

@@ -59,7 +59,8 @@ public:
 
 private:
     struct RefIndex {
-        std::unordered_map<uint32_t, std::vector<VRange>> bins;
+        std::unordered_map<uint32_t, std::vector<VRange>> bins;   // levels 0-4 and the pseudo-bin
+        std::vector<VRange> leaf;                                   // level 5 (16 kb bins): [first chunk beg, last chunk end) per window
         std::vector<uint64_t> linear;
     };
     void parse_header();

@@ -68,15 +68,15 @@ struct PinBuf {
 struct DeviceCtx {
     int dev = 0;
     bool init = false;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
     DevBuf tab[5], c0, c1, tiles_i32, tiles_i64, out, scalars;
     DevBuf raw_all, offs_all, batch_table;      // resident raw bytes of a staged session
-    DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
+    DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
     PinBuf h_total;
-    cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {};
+    cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
     PinBuf h_scalars, h_out[2], h_tiles;
     cudaEvent_t ev_d2h[2] = {};
     std::vector<cudaEvent_t> ev_pool;
@@ -88,6 +88,7 @@ struct DeviceCtx {
         BSG_CUDA(cudaSetDevice(dev));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
         for (int i = 0; i < kSlots; ++i) {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
@@ -96,6 +97,8 @@ struct DeviceCtx {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_total[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_gfree[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_inflated[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_crc[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < kSlots; ++i) BSG_CUDA(cudaEventCreateWithFlags(&ev_pin[i], cudaEventDisableTiming));
         h_total.ensure(64);
@@ -125,14 +128,15 @@ struct DeviceCtx {
         h_out[0].release(); h_out[1].release(); h_tiles.release();
         cudaEventDestroy(ev_d2h[0]); cudaEventDestroy(ev_d2h[1]);
         for (int i = 0; i < 2; ++i) {
-            g_comp[i].release(); g_raw[i].release(); g_offs[i].release(); g_blocks[i].release(); g_walkers[i].release();
+            g_comp[i].release(); g_raw[i].release(); g_offs[i].release(); g_blocks[i].release(); g_crc[i].release(); g_walkers[i].release();
             g_counts[i].release(); g_base[i].release(); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_gfree[i]);
+            cudaEventDestroy(ev_inflated[i]); cudaEventDestroy(ev_crc[i]);
         }
         for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev_pin[i]);
         g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
-        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp);
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux);
         init = false;
     }
 };
@@ -311,6 +315,32 @@ public:
         kt_.decode.push_back(sp); kt_.launches += 1;
     }
 
+    // The caller's flat output buffer is usually freshly allocated (np.empty / R allocVector): its pages fault in on
+    // first touch, which would otherwise happen inside the final D2H scatter.  Touch them on the worker pool now,
+    // while the GPU is busy inflating (the workers are mostly idle in that phase).
+    void prefault_output(int32_t* out, int64_t total) {
+        if (!out || total < (int64_t(1) << 22)) return;
+        const size_t bytes = size_t(total) * 4, piece = size_t(8) << 20;
+        const int n = int((bytes + piece - 1) / piece);
+        {
+            std::lock_guard<std::mutex> g(pf_m_);
+            pf_left_ += n;
+        }
+        volatile uint8_t* base = reinterpret_cast<volatile uint8_t*>(out);
+        for (int k = 0; k < n; ++k)
+            pool_->submit([this, base, bytes, piece, k](int) {
+                const size_t lo = size_t(k) * piece, hi = std::min(bytes, lo + piece);
+                for (size_t o = lo; o < hi; o += 4096) base[o] = 0;
+                std::lock_guard<std::mutex> g(pf_m_);
+                if (--pf_left_ == 0) pf_cv_.notify_all();
+            });
+    }
+    void wait_prefault() {
+        std::unique_lock<std::mutex> lk(pf_m_);
+        pf_cv_.wait(lk, [&] { return pf_left_ == 0; });
+    }
+    ~Session() { wait_prefault(); }
+
     // Tiles depend only on the regions and on (mode, binsize, ss, layout): build + upload them before any device
     // work of the call is queued, and keep them for the next call of a staged session.
     void prepare_tiles(Mode mode, int32_t binsize, int ss, const int64_t* out_offsets) {
@@ -394,6 +424,7 @@ public:
         BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
 
         // result: device -> pinned ring -> caller memory (copies of chunk k+1 overlap the host scatter of chunk k)
+        wait_prefault();
         const double t_d2h = now_ms();
         if (want_output && total > 0) {
             if (!out && !out_ptrs) fail(BSG_EARG, "either out or out_ptrs must be given");
@@ -436,6 +467,7 @@ public:
     }
 
     void check_status(uint32_t status) {
+        if (status & STATUS_BAD_CRC) fail(BSG_EFORMAT, "BGZF CRC32 mismatch in " + bam_.path());
         if (status & STATUS_BAD_DEFLATE) fail(BSG_EFORMAT, "BGZF inflate failed (corrupt DEFLATE stream or ISIZE mismatch) in " + bam_.path());
         if (status & STATUS_CORRUPT) fail(BSG_EFORMAT, "corrupt BAM record chain in " + bam_.path());
         if (status & STATUS_UNSORTED) fail(BSG_EUNSORTED, "BAM file is not coordinate-sorted: " + bam_.path());
@@ -657,12 +689,14 @@ private:
                 BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
             }
+            if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_crc[p.slot], 0));
             BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], c.s_comp));
             n_rows_ += n;
             p.valid = false;
         };
         double t_desc = 0, t_copy = 0, t_wait = 0, t_finish = 0;
         std::vector<InflateBlock> blocks;
+        std::vector<uint32_t> crcs;
         std::vector<uint2> walkers;
         struct CopyPiece { uint64_t file_off, dst_off, len; };
         std::vector<CopyPiece> pieces;
@@ -672,7 +706,7 @@ private:
             const int slot = int(bi & 1);
             // ---- descriptors -----------------------------------------------------------------------------------------
             double tt = now_ms();
-            blocks.clear(); walkers.clear(); pieces.clear();
+            blocks.clear(); crcs.clear(); walkers.clear(); pieces.clear();
             uint64_t ubase = 0, cbase = 0;
             for (size_t k = b->seg_first; k < b->seg_last; ++k) {
                 const Segment& sg = segs_[k];
@@ -687,6 +721,7 @@ private:
                 for (const BlockInfo& blk : sg.blocks) {
                     while (it != ent.end() && (*it >> 16) < blk.coff) ++it;      // stale entries cost parallelism, not correctness
                     blocks.push_back(InflateBlock{uint32_t(cbase + (blk.coff - fbeg) + blk.hdr), blk.csize - blk.hdr - 8, uint32_t(u), blk.isize});
+                    crcs.push_back(blk.crc);
                     for (; it != ent.end() && *it < sg.vend && (*it >> 16) == blk.coff; ++it) {
                         const uint64_t uo = *it & 0xffff;
                         if (uo > blk.isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam_.path());
@@ -706,6 +741,7 @@ private:
             t_wait += now_ms() - tt; tt = now_ms();
             c.g_comp[slot].ensure(cbase + 4096);   // slack: the bit reader looks ahead, and a corrupt stream may run on for one round
             c.g_blocks[slot].ensure(blocks.size() * sizeof(InflateBlock) + 64);
+            c.g_crc[slot].ensure(crcs.size() * 4 + 64);
             c.g_walkers[slot].ensure(walkers.size() * sizeof(uint2) + 64);
             c.g_counts[slot].ensure(walkers.size() * 4 + 64);
             c.g_base[slot].ensure(walkers.size() * 4 + 64);
@@ -753,6 +789,7 @@ private:
                 }
             }
             if (!blocks.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_blocks[slot].p, blocks.data(), blocks.size() * sizeof(InflateBlock), cudaMemcpyHostToDevice, c.s_copy));
+            if (!crcs.empty() && opts_.verify_crc) BSG_CUDA(cudaMemcpyAsync(c.g_crc[slot].p, crcs.data(), crcs.size() * 4, cudaMemcpyHostToDevice, c.s_copy));
             if (!walkers.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, walkers.data(), walkers.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.s_copy));
             BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
             BSG_CUDA(cudaStreamSynchronize(c.s_copy));                 // blocks/walkers vectors are reused next iteration
@@ -763,6 +800,16 @@ private:
             BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
             launch_inflate(c.g_blocks[slot].as<InflateBlock>(), int(blocks.size()), c.g_comp[slot].as<uint8_t>(), d_raw,
                            c.scalars.as<DeviceScalars>(), c.s_comp);
+            if (opts_.verify_crc) {
+                // integrity check on a side stream: it only reads the inflated bytes, so it overlaps walk + decode of this
+                // batch and the inflate of the next one; the slot is not recycled before it has finished (finish()).
+                BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
+                BSG_CUDA(cudaStreamWaitEvent(c.s_aux, c.ev_inflated[slot], 0));
+                launch_crc32(c.g_blocks[slot].as<InflateBlock>(), c.g_crc[slot].as<uint32_t>(), int(blocks.size()), d_raw,
+                             c.scalars.as<DeviceScalars>(), c.s_aux);
+                BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
+                kt_.launches += blocks.empty() ? 0 : 1;
+            }
             Span spw{c.timing_event(), sp.b};
             BSG_CUDA(cudaEventRecord(spw.a, c.s_comp));
             walk_spans.push_back(spw);
@@ -831,6 +878,10 @@ private:
     int64_t rows_cap_ = 0, n_rows_ = 0;
     bool keep_raw_ = false;
     int resident_chunks_ = 0;
+    // background pre-faulting of the caller's output buffer
+    std::mutex pf_m_;
+    std::condition_variable pf_cv_;
+    int pf_left_ = 0;
     // cached tiles
     bool tiles_valid_ = false;
     Mode tiles_mode_ = MODE_COUNT;
@@ -907,6 +958,7 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
         s.prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
+        if (out && out_offsets) s.prefault_output(out, out_offsets[R]);
         s.stage(ext, false);
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
         s.count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, out, out_offsets, out_ptrs, true);
@@ -922,6 +974,7 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
         const double t0 = now_ms();
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         s.prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
+        if (out && out_offsets) s.prefault_output(out, out_offsets[R]);
         s.stage(ext_coverage(tlen_filter, tspan), false);
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
         s.count(MODE_COVERAGE, fp, 1, 0, out, out_offsets, out_ptrs, true);

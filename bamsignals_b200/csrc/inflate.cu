@@ -865,6 +865,40 @@ __global__ void __launch_bounds__(kQ2Warps * 32, 7) k_inflate_q2(const InflateBl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_crc32: BGZF integrity check on the device (htslib verifies the CRC32 of every inflated block; so do we).
+// One thread per block, slicing-by-4 over the block's bytes with the four 256-entry tables in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_crc32(const InflateBlock* __restrict__ blocks, const uint32_t* __restrict__ want, int n_blocks,
+                                               const uint8_t* __restrict__ raw, DeviceScalars* sc) {
+    __shared__ uint32_t tab[4][256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = uint32_t(i);
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        tab[0][i] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = tab[0][i];
+        for (int t = 1; t < 4; ++t) { c = tab[0][c & 0xffu] ^ (c >> 8); tab[t][i] = c; }
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const InflateBlock blk = blocks[b];
+    const uint8_t* p = raw + blk.out_off;
+    uint32_t n = blk.out_len, crc = 0xffffffffu;
+    while (n && (reinterpret_cast<uintptr_t>(p) & 3)) { crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8); --n; }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    for (; n >= 4; n -= 4) {
+        crc ^= *w++;
+        crc = tab[3][crc & 0xffu] ^ tab[2][(crc >> 8) & 0xffu] ^ tab[1][(crc >> 16) & 0xffu] ^ tab[0][crc >> 24];
+    }
+    p = reinterpret_cast<const uint8_t*>(w);
+    while (n--) crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8);
+    if (~crc != want[b]) atomicOr(&sc->status, STATUS_BAD_CRC);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // record-boundary walk
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* raw, uint32_t off) {
@@ -970,6 +1004,12 @@ void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d
     } else {
         launch_ms<8, 10, 8, 2>(d_blocks, n_blocks, d_comp, d_raw, sc, s);
     }
+}
+
+void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
+                  cudaStream_t s) {
+    if (n_blocks <= 0) return;
+    k_crc32<<<(n_blocks + 127) / 128, 128, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
 }
 
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,

@@ -51,7 +51,7 @@ struct DeviceScalars {
     unsigned long long kept;
     unsigned long long candidates;
 };
-enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u, STATUS_BAD_DEFLATE = 4u };
+enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u, STATUS_BAD_DEFLATE = 4u, STATUS_BAD_CRC = 8u };
 
 constexpr int kTileInts = 8192;   // int32 per counting tile (32 KiB of shared memory)
 
@@ -81,6 +81,9 @@ struct InflateBlock {
 };
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s);
+// CRC32 of every inflated block against the BGZF trailer (d_crc[i] belongs to d_blocks[i]).
+void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
+                  cudaStream_t s);
 // Record-boundary walk from index entry points: walkers[w] = (begin, end) byte positions in d_raw.  Two passes
 // (count, scan, write) fill d_offs[0..total] (+ end sentinel) and *d_total.
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,

@@ -1,6 +1,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <numeric>
 
@@ -92,6 +93,9 @@ void scan_segment(const BamFile& bam, Segment* s) {
 
 void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg_cbytes, Pool& pool,
                 std::vector<Segment>* segs) {
+    const bool dbg = getenv("BSG_DEBUG") != nullptr;
+    double t0 = now_ms();
+    auto lap = [&](const char* what) { if (dbg) { const double t = now_ms(); fprintf(stderr, "[bsg]   plan: %s %.1f ms\n", what, t - t0); t0 = t; } };
     struct Q { int32_t rid; int64_t beg, end; };
     std::vector<Q> qs;
     qs.reserve(rg.R);
@@ -101,6 +105,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         if (e > b) qs.push_back(Q{rg.rid[i], b, e});
     }
     std::sort(qs.begin(), qs.end(), [](const Q& a, const Q& b) { return a.rid != b.rid ? a.rid < b.rid : a.beg < b.beg; });
+    lap("sort regions");
     std::vector<VRange> ranges;
     for (size_t i = 0; i < qs.size();) {
         Q cur = qs[i];
@@ -111,6 +116,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         bam.query(cur.rid, cur.beg, cur.end, &ranges);
         i = j;
     }
+    lap("index queries");
     std::sort(ranges.begin(), ranges.end(), [](const VRange& a, const VRange& b) { return a.beg < b.beg; });
     std::vector<VRange> merged;
     for (const VRange& r : ranges) {
@@ -132,6 +138,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
             }
         Segment s; s.vbeg = cur; s.vend = r.end; segs->push_back(std::move(s));
     }
+    lap("merge + split");
     std::mutex em; Error first{0, ""};
     pool.parallel_for(int64_t(segs->size()), 1, [&](int64_t a, int64_t b, int) {
         for (int64_t k = a; k < b; ++k) {
@@ -139,6 +146,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
             catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }
         }
     });
+    lap("block scan");
     if (first.code) throw first;
 }
 

@@ -213,8 +213,7 @@ public:
         : bamp_(open_bam(bampath)), bam_(*bamp_) {
         if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) opts_ = *opts;
         else { memset(&opts_, 0, sizeof opts_); opts_.verify_crc = 1; }
-        if (const char* e = getenv("BSG_GPU_INFLATE")) opts_.gpu_inflate = atoi(e);   // experiment switches
-        if (const char* e = getenv("BSG_BATCH_MB")) opts_.batch_bytes = int64_t(atoll(e)) << 20;
+        if (const char* e = getenv("BSG_BATCH_MB")) opts_.batch_bytes = int64_t(atoll(e)) << 20;   // experiment switch
         resolve_regions(bam_, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg_);
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -236,7 +235,7 @@ public:
         keep_raw_ = keep_raw;
         segs_.clear();
         plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
-        const bool gpu = opts_.gpu_inflate != 0;
+        const bool gpu = opts_.gpu_inflate >= 0;       // 0 = default = device inflate; -1 = host zlib pool
         const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : (gpu ? kDefaultGpuBatch : kDefaultBatch);
         // group segments into batches
         batches_.clear();

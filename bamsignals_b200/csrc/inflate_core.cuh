@@ -246,3 +246,4 @@ BSG_HD int fill_queue(BitReader& br, const Tables& T, Q q, uint32_t* op_dec, int
 
 }  // namespace inflate_core
 }  // namespace bsg
+

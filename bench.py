@@ -108,7 +108,7 @@ def run_ours(args, rank, world, local_rank):
     gr_all, kw, fn = WL.regions(preset, gs)
     gr, _ = WL.shard_regions(gr_all, rank, world)
     ca = B.core_args(fn, **kw)
-    gpu_inflate = int(os.environ.get("BSG_GPU_INFLATE", "1" if args.gpu_inflate else "0"))
+    gpu_inflate = 1 if args.gpu_inflate else -1
     opts = B.default_opts(devices=[local_rank], inflate_threads=max(1, (os.cpu_count() or 1) // world), gpu_inflate=gpu_inflate)
     is_cov = fn == "bamCoverage"
     ext = (ca["tlen_filter"][1] if (is_cov and ca["tspan"]) else 0) if is_cov else \
@@ -210,7 +210,9 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(preset, {}).get(dom)
+        t_ent = json.load(open(tpath)).get(preset, {}).get(dom)
+        if t_ent and "dram_bytes_per_read" in t_ent:       # ncu capture at a smaller scale, per record of the launch
+            traffic = t_ent["dram_bytes_per_read"] * reads_all * per
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": round(kern[dom]["gbs"] / peak, 4) if kern[dom]["gbs"] else None, "traffic": traffic,
                 "peak_source": peak_src, "kernels": kern,
@@ -232,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "reads/s", "reads_decoded_per_step": int(reads_e2e), "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "breakdown_ms_rank0": {k: round(te[k], 2) for k in ("ms_plan", "ms_fetch", "ms_h2d", "ms_inflate_gpu", "ms_d2h", "ms_kernels", "ms_total")},
-                "inflate": "gpu" if gpu_inflate else "host zlib",
+                "inflate": "gpu" if gpu_inflate > 0 else "host zlib",
                 "note": "BAM file in page cache -> result in host memory; inflate (GPU kernel or host zlib pool) is inside"},
         "gpu_launches": int(launches_all),
         "wall_ms_per_step": wall_ms / args.steps,

@@ -60,10 +60,11 @@ typedef struct bsg_opts {
     int32_t n_devices;        /* 0 = use device 0 only; >0 = devices[0..n) (regions sharded, no collective) */
     int32_t devices[16];
     int32_t inflate_threads;  /* host inflate / record-walk workers; 0 = all hardware threads */
-    int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (64 MiB) */
-    int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does) */
+    int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (1 GiB device inflate, 64 MiB host) */
+    int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does); on by default */
     int32_t use_cache;        /* keep the decoded read table of the last BAM resident in HBM across calls */
-    int32_t gpu_inflate;      /* 1 = inflate BGZF blocks on the device (host ships compressed bytes) */
+    int32_t gpu_inflate;      /* 0 (default) or 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the
+                                 device (the host only ships compressed bytes); -1: host zlib worker pool */
     int32_t reserved[8];
 } bsg_opts;
 

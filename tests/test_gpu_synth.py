@@ -32,9 +32,10 @@ def gen_dir(tmp_path_factory):
 @pytest.mark.parametrize("preset,gs,record", [("c2", 0.002, "compact"), ("c2", 0.001, "realistic"), ("c3", 0.004, "compact"),
                                               ("c3", 0.002, "realistic"), ("c4", 0.002, "compact"), ("c5", 0.002, "compact")])
 def test_scaled_configs(gen_dir, preset, gs, record):
+    """host-inflate path (zlib worker pool -> pinned staging -> H2D); the device-inflate twin is further down"""
     bam, info = WL.make_bam(preset, gs, gen_dir, record=record, unplaced=7)
     gr, kw, fn = WL.regions(preset, gs)
-    got = getattr(B, fn)(bam, gr, **kw)
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(gpu_inflate=-1), **kw)
     t = B.timings()
     want = getattr(O, fn)(bam, gr, nthreads=8, **kw)
     assert np.array_equal(WL.as_flat(got), WL.as_flat(want))
@@ -47,9 +48,9 @@ def test_batching_does_not_change_results(gen_dir, batch_bytes, threads):
     bam, _ = WL.make_bam("c4", 0.002, gen_dir, unplaced=7)
     gr, kw, fn = WL.regions("c4", 0.002)
     ref = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
-    got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch_bytes, inflate_threads=threads), **kw)
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch_bytes, inflate_threads=threads, gpu_inflate=-1), **kw)
     assert np.array_equal(WL.as_flat(got), ref)
-    assert B.timings()["n_batches"] >= (2 if batch_bytes < (1 << 22) else 1)
+    assert B.timings()["n_batches"] >= (2 if batch_bytes < (1 << 22) else 1) and B.timings()["ms_inflate_gpu"] == 0
 
 
 def test_all_apis_on_paired_synthetic(gen_dir):
@@ -124,13 +125,15 @@ def test_corrupt_bgzf_is_an_error(tmp_path, fixture_bam):
     open(p, "wb").write(raw)
     open(p + ".bai", "wb").write(open(fixture_bam + ".bai", "rb").read())
     gr = B.GRanges(["chr1", "chr2", "chr3"], [1, 1, 1], [10000] * 3)
-    with pytest.raises(B.BamsignalsError) as e:
-        B.bamCount(p, gr)
-    assert e.value.code == -4
+    for mode in (-1, 1):
+        with pytest.raises(B.BamsignalsError) as e:
+            B.bamCount(p, gr, opts=B.default_opts(gpu_inflate=mode))
+        assert e.value.code == -4
     open(p, "wb").write(raw[:700000])                     # truncated mid-block
-    with pytest.raises(B.BamsignalsError) as e:
-        B.bamCount(p, gr)
-    assert e.value.code == -4
+    for mode in (-1, 1):
+        with pytest.raises(B.BamsignalsError) as e:
+            B.bamCount(p, gr, opts=B.default_opts(gpu_inflate=mode))
+        assert e.value.code == -4
     # the library is still usable after an error
     assert np.array_equal(B.bamCount(fixture_bam, gr), O.bamCount(fixture_bam, gr))
 

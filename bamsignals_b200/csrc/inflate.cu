@@ -33,12 +33,15 @@ constexpr unsigned FULL = 0xffffffffu;
 // The decode core is unit-tested on the host (tests/host_inflate_harness.cpp) against zlib's CRC32.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kQ2Warps = 4;
+#ifndef BSG_Q2_MINB
+#define BSG_Q2_MINB 7
+#endif
 struct Q2Smem {
     inflate_core::Tables T;
     uint32_t q[inflate_core::kQueue];
 };
 
-__global__ void __launch_bounds__(kQ2Warps * 32, 7) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
+__global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
                                                                   const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
     __shared__ Q2Smem s_mem[kQ2Warps];

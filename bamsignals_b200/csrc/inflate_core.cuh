@@ -13,7 +13,10 @@
 namespace bsg {
 namespace inflate_core {
 
-constexpr int kLitBits = 10, kDistBits = 8;
+#ifndef BSG_LIT_BITS
+#define BSG_LIT_BITS 10
+#endif
+constexpr int kLitBits = BSG_LIT_BITS, kDistBits = 8;
 constexpr int kQueue = 256;
 
 // token: literal = byte ; match = 1 << 31 | (dist - 1) << 16 | len ; skip (stored bytes already in place) = 1 << 30 | len

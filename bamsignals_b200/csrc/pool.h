@@ -34,6 +34,14 @@ public:
         }
         cv_.notify_one();
     }
+    // background work: only runs when no regular task is waiting
+    void submit_low(std::function<void(int)> f) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            low_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
 
     // Run f(i, worker) for i in [0,n) on the pool and wait (the caller does not participate).
     void parallel_for(int64_t n, int64_t grain, const std::function<void(int64_t, int64_t, int)>& f) {
@@ -60,16 +68,16 @@ private:
             std::function<void(int)> f;
             {
                 std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
-                if (q_.empty()) return;
-                f = std::move(q_.front());
-                q_.pop_front();
+                cv_.wait(lk, [&] { return stop_ || !q_.empty() || !low_.empty(); });
+                if (!q_.empty()) { f = std::move(q_.front()); q_.pop_front(); }
+                else if (!low_.empty()) { f = std::move(low_.front()); low_.pop_front(); }
+                else return;
             }
             f(idx);
         }
     }
     std::vector<std::thread> threads_;
-    std::deque<std::function<void(int)>> q_;
+    std::deque<std::function<void(int)>> q_, low_;
     std::mutex m_;
     std::condition_variable cv_;
     bool stop_ = false;

@@ -245,6 +245,16 @@ int64_t BamFile::bp_per_block(int tid) const {
     return int64_t(std::min(16.0e6, std::max(16384.0, bp)));
 }
 
+uint64_t BamFile::approx_coffset(int tid, int64_t pos) const {
+    // offsets grow with (tid, pos) in a coordinate-sorted file; references without reads inherit the next one's start
+    for (int t = std::max(tid, 0); t < int(refs_.size()); ++t) {
+        const auto& lin = refs_[t].linear;
+        size_t w = t == tid ? size_t(std::max<int64_t>(0, pos) >> 14) : 0;
+        for (; w < lin.size(); ++w) if (lin[w]) return lin[w] >> 16;
+    }
+    return size_;
+}
+
 bool BamFile::index_unchanged() const {
     struct stat st;
     if (::stat(index_path_.c_str(), &st) != 0) return false;

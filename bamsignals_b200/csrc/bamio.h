@@ -49,6 +49,10 @@ public:
     // index's (ref_beg, ref_end) file offsets: index queries closer than this fetch the same blocks anyway.
     int64_t bp_per_block(int tid) const;
 
+    // Approximate compressed file offset of the first record at or after (tid, pos), from the linear index
+    // (used only to balance region shards across devices).
+    uint64_t approx_coffset(int tid, int64_t pos) const;
+
     // Sorted, de-duplicated record-aligned virtual offsets known to the index (linear index entries, chunk
     // begins/ends, first record): independent entry points for parallel inflate + record walking.
     const std::vector<uint64_t>& entry_points() const { return entries_; }

@@ -228,6 +228,21 @@ public:
         tm_.n_devices = 1;
     }
 
+    // One shard of a multi-device call: regions already resolved, device chosen by the caller.
+    Session(std::shared_ptr<BamFile> bam, Regions rg, const bsg_opts& o, int dev)
+        : bamp_(std::move(bam)), bam_(*bamp_), opts_(o), rg_(std::move(rg)) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+            fail(BSG_ECUDA, "no CUDA device available (libbamsignals_cuda has no CPU fallback)");
+        if (dev < 0 || dev >= ndev || dev >= 16) fail(BSG_EARG, "invalid CUDA device index");
+        ctx_ = &g_ctx[dev];
+        ctx_->ensure_init(dev);
+        ctx_->ev_next = 0;
+        pool_ = &get_pool(opts_.inflate_threads);
+        memset(&tm_, 0, sizeof tm_);
+        tm_.n_devices = 1;
+    }
+
     // Fetch + upload (+ decode unless keep_raw) everything the regions need with halo `ext`.
     void stage(int64_t ext, bool keep_raw) {
         if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
@@ -493,6 +508,7 @@ public:
         kt_ = KernelTimes();
         ctx_->ev_next = 0;
     }
+    const bsg_timings& timings() const { return tm_; }
     void reset_counters() { int nd = tm_.n_devices; int64_t bc = tm_.bytes_compressed, bi = tm_.bytes_inflated, nb = tm_.n_batches;
         memset(&tm_, 0, sizeof tm_); tm_.n_devices = nd; tm_.bytes_compressed = bc; tm_.bytes_inflated = bi; tm_.n_batches = nb; }
 
@@ -920,6 +936,103 @@ int64_t ext_coverage(const int32_t* tlen_filter, int32_t tspan) {
     return tspan ? int64_t(tlen_filter[1]) : 0;                                       // src/bamsignals.cpp:487
 }
 
+bsg_opts effective_opts(const bsg_opts* opts) {
+    bsg_opts o;
+    if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) o = *opts;
+    else { memset(&o, 0, sizeof o); o.verify_crc = 1; }
+    return o;
+}
+
+// A call on several devices: the regions are cut into contiguous shards in (chromosome, start) order, balanced by
+// the compressed bytes between their index positions; every shard runs the whole pipeline on its own device in its
+// own host thread and writes straight into the caller's per-region destinations.  No exchange step, no collective:
+// every output element has exactly one owner.
+void run_multi_device(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                      const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                      const bsg_opts& o, Mode mode, const FilterParams& fp, int32_t binsize, int ss, int64_t ext,
+                      int32_t* out, const int64_t* out_offsets, int32_t* const* out_ptrs, double t0) {
+    if (!out_offsets) fail(BSG_EARG, "out_offsets is required");
+    if (!out && !out_ptrs) fail(BSG_EARG, "either out or out_ptrs must be given");
+    const int nd = o.n_devices;
+    std::shared_ptr<BamFile> bam = open_bam(bampath);
+    Regions rg;
+    resolve_regions(*bam, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg);
+    std::vector<int64_t> order(R);
+    for (int64_t i = 0; i < R; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        return rg.rid[a] != rg.rid[b] ? rg.rid[a] < rg.rid[b] : (rg.loc[a] != rg.loc[b] ? rg.loc[a] < rg.loc[b] : a < b);
+    });
+    // cut points at equal compressed-byte quantiles of the regions' index positions
+    std::vector<int64_t> cut(nd + 1, R);
+    cut[0] = 0;
+    if (R > 0) {
+        std::vector<uint64_t> off(R);
+        for (int64_t k = 0; k < R; ++k) off[k] = bam->approx_coffset(rg.rid[order[k]], rg.loc[order[k]]);
+        for (int64_t k = 1; k < R; ++k) off[k] = std::max(off[k], off[k - 1]);
+        const uint64_t lo = off.front(), hi = std::max(off.back(), lo + 1);
+        for (int d = 1; d < nd; ++d) {
+            const uint64_t target = lo + (hi - lo) * uint64_t(d) / uint64_t(nd);
+            int64_t c = std::lower_bound(off.begin(), off.end(), target) - off.begin();
+            c = std::max(c, R * d / (4 * nd));                    // never starve a device completely on odd indexes
+            cut[d] = std::max(cut[d - 1], std::min<int64_t>(c, R));
+        }
+    }
+    get_pool(o.inflate_threads);                                   // create the shared worker pool before the device threads race for it
+    std::vector<bsg_timings> tms(nd);
+    std::vector<Error> errs(nd, Error{0, ""});
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d)
+        th.emplace_back([&, d] {
+            try {
+                const int64_t n = cut[d + 1] - cut[d];
+                Regions sub;
+                sub.R = n;
+                sub.rid.resize(n); sub.loc.resize(n); sub.width.resize(n); sub.strand.resize(n);
+                std::vector<int64_t> loff(n + 1, 0);
+                std::vector<int32_t*> lptr(n);
+                for (int64_t k = 0; k < n; ++k) {
+                    const int64_t i = order[cut[d] + k];
+                    sub.rid[k] = rg.rid[i]; sub.loc[k] = rg.loc[i]; sub.width[k] = rg.width[i]; sub.strand[k] = rg.strand[i];
+                    loff[k + 1] = loff[k] + (out_offsets[i + 1] - out_offsets[i]);
+                    lptr[k] = out ? out + out_offsets[i] : out_ptrs[i];
+                }
+                Session s(bam, std::move(sub), o, o.devices[d]);
+                s.prepare_tiles(mode, binsize, ss, loff.data());
+                s.stage(ext, false);
+                s.count(mode, fp, binsize, ss, nullptr, loff.data(), lptr.data(), true);
+                s.finish_timings(t0);
+                tms[d] = s.timings();
+            } catch (Error& e) { errs[d] = e; }
+            catch (std::exception& e) { errs[d] = Error{BSG_EARG, std::string("internal error: ") + e.what()}; }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : errs) if (e.code) throw e;
+    // aggregate: counters add up, times are the slowest device's
+    bsg_timings a;
+    memset(&a, 0, sizeof a);
+    for (const bsg_timings& t : tms) {
+        a.records += t.records; a.records_kept += t.records_kept; a.bytes_compressed += t.bytes_compressed;
+        a.bytes_inflated += t.bytes_inflated; a.candidates += t.candidates; a.out_elems += t.out_elems;
+        a.n_tiles += t.n_tiles; a.n_batches += t.n_batches; a.n_launches += t.n_launches;
+        a.ms_plan = std::max(a.ms_plan, t.ms_plan); a.ms_fetch = std::max(a.ms_fetch, t.ms_fetch);
+        a.ms_h2d = std::max(a.ms_h2d, t.ms_h2d); a.ms_d2h = std::max(a.ms_d2h, t.ms_d2h);
+        a.ms_decode = std::max(a.ms_decode, t.ms_decode); a.ms_filter = std::max(a.ms_filter, t.ms_filter);
+        a.ms_join = std::max(a.ms_join, t.ms_join); a.ms_count = std::max(a.ms_count, t.ms_count);
+        a.ms_inflate_gpu = std::max(a.ms_inflate_gpu, t.ms_inflate_gpu); a.ms_kernels = std::max(a.ms_kernels, t.ms_kernels);
+        a.ms_device = std::max(a.ms_device, t.ms_device);
+    }
+    a.n_devices = nd;
+    a.ms_total = now_ms() - t0;
+    g_tm = a;
+}
+
+void validate_devices(const bsg_opts& o) {
+    if (o.n_devices < 0 || o.n_devices > 16) fail(BSG_EARG, "n_devices must be between 0 and 16");
+    for (int a = 0; a < o.n_devices; ++a)
+        for (int b = a + 1; b < o.n_devices; ++b)
+            if (o.devices[a] == o.devices[b]) fail(BSG_EARG, "the same CUDA device is listed twice");
+}
+
 template <class F>
 int guarded(F&& f) {
     try {
@@ -957,6 +1070,14 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
                const bsg_opts* opts) {
     return guarded([&] {
         const double t0 = now_ms();
+        const bsg_opts o = effective_opts(opts);
+        validate_devices(o);
+        if (o.n_devices > 1) {
+            run_multi_device(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, o,
+                             binsize <= 0 ? MODE_COUNT : MODE_PROFILE, make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0),
+                             binsize, ss != 0, ext_pileup(tlen_filter, shift, pe_mid), out, out_offsets, out_ptrs, t0);
+            return;
+        }
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
         s.prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
@@ -974,6 +1095,14 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
                  const int64_t* out_offsets, int32_t* const* out_ptrs, const bsg_opts* opts) {
     return guarded([&] {
         const double t0 = now_ms();
+        const bsg_opts o = effective_opts(opts);
+        validate_devices(o);
+        if (o.n_devices > 1) {
+            run_multi_device(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, o, MODE_COVERAGE,
+                             make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan), 1, 0,
+                             ext_coverage(tlen_filter, tspan), out, out_offsets, out_ptrs, t0);
+            return;
+        }
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         s.prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
         if (out && out_offsets) s.request_prefault(out, out_offsets[R]);

@@ -219,7 +219,7 @@ public:
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
             fail(BSG_ECUDA, "no CUDA device available (libbamsignals_cuda has no CPU fallback)");
         int dev = opts_.n_devices > 0 ? opts_.devices[0] : 0;
-        if (dev < 0 || dev >= ndev) fail(BSG_EARG, "invalid CUDA device index");
+        if (dev < 0 || dev >= ndev || dev >= 16) fail(BSG_EARG, "invalid CUDA device index");
         ctx_ = &g_ctx[dev];
         ctx_->ensure_init(dev);
         ctx_->ev_next = 0;

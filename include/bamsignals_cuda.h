@@ -57,12 +57,14 @@ extern "C" {
 /* Execution options; none of them changes results.  Zero-initialise, set struct_size = sizeof(bsg_opts). */
 typedef struct bsg_opts {
     int32_t struct_size;
-    int32_t n_devices;        /* 0 = use device 0 only; >0 = devices[0..n) (regions sharded, no collective) */
+    int32_t n_devices;        /* 0 = device 0 only; 1..16 = devices[0..n): regions are sharded over the devices inside the
+                                 call, one host thread + pipeline per device, no collective */
     int32_t devices[16];
     int32_t inflate_threads;  /* host inflate / record-walk workers; 0 = all hardware threads */
     int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (1 GiB device inflate, 64 MiB host) */
     int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does); on by default */
-    int32_t use_cache;        /* keep the decoded read table of the last BAM resident in HBM across calls */
+    int32_t use_cache;        /* reserved, must be 0 (open BAM handles and buffers are always reused across calls;
+                                 record data is never cached: every call reads, inflates and decodes the file again) */
     int32_t gpu_inflate;      /* 0 (default) or 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the
                                  device (the host only ships compressed bytes); -1: host zlib worker pool */
     int32_t reserved[8];

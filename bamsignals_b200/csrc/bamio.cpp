@@ -199,6 +199,13 @@ void BamFile::load_index() {
             } else {
                 for (auto& c : cs) { entries_.push_back(c.beg); entries_.push_back(c.end); }
             }
+            if (bin != 37450)
+                for (auto& c : cs) {
+                    if (c.end <= c.beg) continue;
+                    if (refs_[r].ref_end <= refs_[r].ref_beg) { refs_[r].ref_beg = c.beg; refs_[r].ref_end = c.end; }
+                    refs_[r].ref_beg = std::min(refs_[r].ref_beg, c.beg);
+                    refs_[r].ref_end = std::max(refs_[r].ref_end, c.end);
+                }
             if (bin >= 4681 && bin < 37449 + 1) {
                 // Leaf bins go into a flat per-window array: the file is coordinate-sorted, so the chunks of a run of
                 // consecutive leaf bins lie between the first bin's first chunk and the last bin's last chunk.
@@ -266,53 +273,25 @@ void BamFile::query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out)
     if (tid < 0 || tid >= int(refs_.size())) return;
     const RefIndex& ri = refs_[tid];
     if (beg < 0) beg = 0;
-    if (end <= beg) return;
-    uint64_t min_off = 0;
+    if (end <= beg || ri.ref_end <= ri.ref_beg) return;
+    // Lower bound L: the linear index gives the first record overlapping the 16 kb window of `beg`; every record
+    // overlapping [beg, ...) lies at or behind it (htslib uses the same bound as `min_off`).
+    uint64_t lo = ri.ref_beg;
     if (!ri.linear.empty()) {
-        size_t w = size_t(beg >> 14);
-        min_off = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
-        // Some indexers leave zero entries for windows no read starts in; walk back to the last filled one.
-        if (min_off == 0 && w < ri.linear.size())
-            for (size_t k = w; k-- > 0;) if (ri.linear[k]) { min_off = ri.linear[k]; break; }
+        const size_t w = size_t(beg >> 14);
+        uint64_t v = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
+        // some indexers leave zero entries for windows no read overlaps; walk back to the last filled one
+        if (v == 0 && w < ri.linear.size())
+            for (size_t k = w; k-- > 0;) if (ri.linear[k]) { v = ri.linear[k]; break; }
+        lo = std::max(lo, v);
     }
-    // Whole-chromosome style queries: the pseudo-bin's (ref_beg, ref_end) is exact and avoids walking 37k bins.
-    int64_t span_bins = (end >> 14) - (beg >> 14);
-    auto meta = ri.bins.find(37450);
-    if (span_bins > 4096 && meta != ri.bins.end() && !meta->second.empty() && meta->second[0].end > meta->second[0].beg) {
-        VRange r = meta->second[0];
-        if (r.beg < min_off) r.beg = min_off;
-        if (r.end > r.beg) out->push_back(r);
-        return;
-    }
-    // levels 0-4: hash lookups (at most 1 + 8 + 64 + 512 + 4096/8 bins for a whole chromosome)
-    int64_t e1 = std::min<int64_t>(end, 1LL << 29) - 1;
-    for (int shift = 26, t = 1; shift >= 17; shift -= 3, t = (t << 3) + 1)
-        for (int64_t k = t + (beg >> shift); k <= t + (e1 >> shift); ++k) {
-            auto it = ri.bins.find(uint32_t(k));
-            if (it == ri.bins.end()) continue;
-            for (const VRange& c : it->second)
-                if (c.end > min_off) out->push_back(VRange{std::max(c.beg, min_off), c.end});
-        }
-    {
-        auto it = ri.bins.find(0);
-        if (it != ri.bins.end())
-            for (const VRange& c : it->second)
-                if (c.end > min_off) out->push_back(VRange{std::max(c.beg, min_off), c.end});
-    }
-    // level 5: one range from the first to the last non-empty window of the query
-    if (!ri.leaf.empty()) {
-        int64_t w0 = beg >> 14, w1 = std::min<int64_t>(e1 >> 14, int64_t(ri.leaf.size()) - 1);
-        while (w0 <= w1 && ri.leaf[size_t(w0)].end == 0) ++w0;
-        while (w1 >= w0 && ri.leaf[size_t(w1)].end == 0) --w1;
-        if (w0 <= w1) {
-            uint64_t lo = ~0ull, hi = 0;
-            // chunk bounds are monotone along a sorted file, but take min/max over the ends to be safe with odd indexers
-            lo = std::min(ri.leaf[size_t(w0)].beg, ri.leaf[size_t(w1)].beg);
-            hi = std::max(ri.leaf[size_t(w0)].end, ri.leaf[size_t(w1)].end);
-            for (int64_t w = w0; w <= w1; ++w) hi = std::max(hi, ri.leaf[size_t(w)].end);
-            if (hi > min_off) out->push_back(VRange{std::max(lo, min_off), hi});
-        }
-    }
+    // Upper bound U: the first record that lies entirely inside a 16 kb window behind the query (first chunk of the
+    // first non-empty leaf bin > window(end-1)) starts at pos >= end, and the file is coordinate-sorted, so nothing at
+    // or behind it can overlap [beg, end).  This plays the role of the iterator's "pos >= end -> stop" rule.
+    uint64_t hi = ri.ref_end;
+    for (size_t w = size_t((end - 1) >> 14) + 1; w < ri.leaf.size(); ++w)
+        if (ri.leaf[w].end) { hi = std::min(hi, ri.leaf[w].beg); break; }
+    if (hi > lo) out->push_back(VRange{lo, hi});
 }
 
 }  // namespace bsg

@@ -41,8 +41,9 @@ public:
     // Parse the block header at `coff`; returns false at EOF (coff == size), throws BSG_EFORMAT on garbage.
     bool block_at(uint64_t coff, BlockInfo* b) const;
 
-    // Record-aligned virtual-offset ranges that contain every record of `tid` overlapping [beg,end) (htslib's
-    // bins + linear-index rule), sorted and merged.  A superset is all the counting path needs.
+    // One record-aligned virtual-offset range that contains every record of `tid` overlapping [beg,end): from the
+    // linear-index lower bound to the first record known to start behind `end`.  A superset is all the counting path
+    // needs; it is at most a 16 kb window wider than what htslib's iterator reads.
     void query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out) const;
 
     // Genomic distance (bp) on `tid` that one maximal BGZF block (64 KiB compressed) covers on average, from the
@@ -66,6 +67,7 @@ private:
         std::unordered_map<uint32_t, std::vector<VRange>> bins;   // levels 0-4 and the pseudo-bin
         std::vector<VRange> leaf;                                   // level 5 (16 kb bins): [first chunk beg, last chunk end) per window
         std::vector<uint64_t> linear;
+        uint64_t ref_beg = 0, ref_end = 0;                          // first chunk begin / last chunk end of the reference
     };
     void parse_header();
     void load_index();

@@ -774,35 +774,41 @@ private:
                 d_offs = c.g_offs[slot].as<uint32_t>();
             }
             // ---- compressed bytes: file (page cache) -> pinned chunk -> device, chunk by chunk ----------------------------
+            // The pinned chunk mirrors a window [c_lo, c_lo + kCompChunk) of the device buffer byte for byte, so every
+            // chunk is ONE H2D copy no matter how many file pieces it holds.
             {
-                // flatten the pieces into kCompChunk-sized uploads
+                struct Part { const uint8_t* src; uint64_t pin_off, len; };
                 size_t pi = 0; uint64_t done_in_piece = 0;
                 while (pi < pieces.size()) {
                     const int ps = pin_slot; pin_slot = (pin_slot + 1) % kSlots;
                     c.h_raw[ps].ensure(kCompChunk + 64);
                     BSG_CUDA(cudaEventSynchronize(c.ev_pin[ps]));
                     uint8_t* pin = c.h_raw[ps].as<uint8_t>();
-                    // gather as many (partial) pieces as fit
-                    struct Part { const uint8_t* src; uint64_t pin_off, dst_off, len; };
-                    std::vector<Part> parts;
-                    uint64_t fill = 0;
-                    while (pi < pieces.size() && fill < kCompChunk) {
+                    const uint64_t c_lo = pieces[pi].dst_off + done_in_piece;
+                    uint64_t c_hi = c_lo;
+                    std::vector<std::vector<Part>> tasks(1);
+                    uint64_t task_bytes = 0;
+                    while (pi < pieces.size()) {
                         const CopyPiece& pc = pieces[pi];
-                        const uint64_t take = std::min<uint64_t>(pc.len - done_in_piece, kCompChunk - fill);
-                        parts.push_back(Part{bam_.data() + pc.file_off + done_in_piece, fill, pc.dst_off + done_in_piece, take});
-                        fill += take; done_in_piece += take;
-                        if (done_in_piece == pc.len) { ++pi; done_in_piece = 0; }
+                        const uint64_t d0 = pc.dst_off + done_in_piece;
+                        if (d0 - c_lo >= kCompChunk) break;
+                        const uint64_t take = std::min<uint64_t>(pc.len - done_in_piece, kCompChunk - (d0 - c_lo));
+                        // split long pieces into <= 1 MiB parts; group short ones into ~1 MiB tasks
+                        for (uint64_t o = 0; o < take; o += (1u << 20)) {
+                            const uint64_t n = std::min<uint64_t>(1u << 20, take - o);
+                            if (task_bytes + n > (1u << 20) && !tasks.back().empty()) { tasks.emplace_back(); task_bytes = 0; }
+                            tasks.back().push_back(Part{bam_.data() + pc.file_off + done_in_piece + o, d0 + o - c_lo, n});
+                            task_bytes += n;
+                        }
+                        c_hi = d0 + take;
+                        done_in_piece += take;
+                        if (done_in_piece == pc.len) { ++pi; done_in_piece = 0; } else break;
                     }
-                    // parallel memcpy into the pinned chunk (1 MiB tasks)
-                    std::vector<Part> tasks;
-                    for (const Part& pt : parts)
-                        for (uint64_t o = 0; o < pt.len; o += (1u << 20))
-                            tasks.push_back(Part{pt.src + o, pt.pin_off + o, 0, std::min<uint64_t>(1u << 20, pt.len - o)});
                     pool_->parallel_for(int64_t(tasks.size()), 1, [&](int64_t a, int64_t e, int) {
-                        for (int64_t t = a; t < e; ++t) memcpy(pin + tasks[t].pin_off, tasks[t].src, tasks[t].len);
+                        for (int64_t t = a; t < e; ++t)
+                            for (const Part& pt : tasks[t]) memcpy(pin + pt.pin_off, pt.src, pt.len);
                     });
-                    for (const Part& pt : parts)
-                        BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + pt.dst_off, pin + pt.pin_off, pt.len, cudaMemcpyHostToDevice, c.s_copy));
+                    BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + c_lo, pin, c_hi - c_lo, cudaMemcpyHostToDevice, c.s_copy));
                     BSG_CUDA(cudaEventRecord(c.ev_pin[ps], c.s_copy));
                 }
             }

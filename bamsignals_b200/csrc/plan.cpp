@@ -62,7 +62,12 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
 
 namespace {
 
-constexpr uint64_t kFuseGapCBytes = 1 << 16;   // compressed bytes
+// Ranges whose compressed gap is at most this many bytes are fused (fetching is block-granular).  0 = only ranges that
+// share or adjoin a BGZF block; larger values trade inflate work for fewer, longer segments.
+uint64_t fuse_gap() {
+    static const uint64_t g = getenv("BSG_FUSE_GAP") ? uint64_t(atoll(getenv("BSG_FUSE_GAP"))) : 0;
+    return g;
+}
 
 void scan_segment(const BamFile& bam, Segment* s) {
     uint64_t c = s->vbeg >> 16;
@@ -110,8 +115,8 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     for (size_t i = 0; i < qs.size();) {
         Q cur = qs[i];
         size_t j = i + 1;
-        // queries closer than the genomic span of one BGZF block would fetch the same blocks: ask the index once
-        const int64_t gap = bam.bp_per_block(cur.rid);
+        // queries closer than a linear-index window read the same records: ask the index once
+        const int64_t gap = 16384;
         for (; j < qs.size() && qs[j].rid == cur.rid && qs[j].beg <= cur.end + gap; ++j) cur.end = std::max(cur.end, qs[j].end);
         bam.query(cur.rid, cur.beg, cur.end, &ranges);
         i = j;
@@ -123,7 +128,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         if (r.end <= r.beg) continue;
         // Ranges that touch the same or neighbouring BGZF blocks are fused: fetching is block-granular, so a gap
         // shorter than a block would only make both neighbours inflate the shared blocks twice.
-        if (!merged.empty() && (r.beg >> 16) <= (merged.back().end >> 16) + kFuseGapCBytes)
+        if (!merged.empty() && (r.beg >> 16) <= (merged.back().end >> 16) + fuse_gap())
             merged.back().end = std::max(merged.back().end, r.end);
         else merged.push_back(r);
     }
@@ -140,7 +145,8 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     }
     lap("merge + split");
     std::mutex em; Error first{0, ""};
-    pool.parallel_for(int64_t(segs->size()), 1, [&](int64_t a, int64_t b, int) {
+    const int64_t grain = std::max<int64_t>(1, int64_t(segs->size()) / (int64_t(pool.size()) * 8));
+    pool.parallel_for(int64_t(segs->size()), grain, [&](int64_t a, int64_t b, int) {
         for (int64_t k = a; k < b; ++k) {
             try { scan_segment(bam, &(*segs)[k]); }
             catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }

@@ -109,28 +109,60 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
             }
             const uint32_t pos = pos_base + incl - len;
             if (valid && !is_match && !is_skip) out[pos] = uint8_t(t);
-            uint32_t mm = __ballot_sync(FULL, is_match);
+            // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
+            // first pending token reads only finished output, so all of them are copied at once, each by its own lane
+            // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
+            // they reach the front.
+            uint32_t pending = __ballot_sync(FULL, is_match);
+            const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
+            const bool is_long = is_match && own_len > 32u;
+            const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
             __syncwarp();
-            while (mm) {
-                const int k = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t mt = __shfl_sync(FULL, t, k);
-                const uint32_t mpos = __shfl_sync(FULL, pos, k);
-                const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
-                uint8_t* dst = out + mpos;
-                if (uint32_t(lane) < mlen) {
-                    // the first 32 bytes never depend on bytes written in this step
-                    const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
-                    dst[lane] = dst[so];
-                }
-                if (mlen > 32u) {
+            while (pending) {
+                const int first = __ffs(pending) - 1;
+                const uint32_t front = __shfl_sync(FULL, pos, first);
+                if (__shfl_sync(FULL, uint32_t(is_long), first)) {
+                    const uint32_t mt = __shfl_sync(FULL, t, first);
+                    const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
+                    uint8_t* dst = out + front;
+                    {   // the first 32 bytes never depend on bytes written in this step
+                        const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
+                        dst[lane] = dst[so];
+                    }
                     // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
                     const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
                     for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
                         __syncwarp();
                         if (j < mlen) dst[j] = dst[int(j) - int(K)];
                     }
+                    pending &= ~(1u << first);
+                    __syncwarp();
+                    continue;
                 }
+                const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
+                if (ready) {
+                    for (uint32_t done = 0; done < own_len; done += 8u) {
+                        const uint32_t n = min(own_len - done, 8u);
+                        uint8_t* d = out + pos + done;
+                        if (pos + done >= 8u) {
+                            const uint8_t* sp = d - max(own_dist, 8u);
+                            uint32_t lo = 0, hi = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { lo |= uint32_t(sp[k]) << (8 * k); hi |= uint32_t(sp[4 + k]) << (8 * k); }
+                            uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
+                            if (own_dist < 8u) {
+                                uint64_t rep = w >> (8u * (8u - own_dist));
+                                for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
+                                w = rep;
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
+                        } else {
+                            for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
+                        }
+                    }
+                }
+                pending &= ~__ballot_sync(FULL, ready);
                 __syncwarp();
             }
             pos_base += __shfl_sync(FULL, incl, 31);

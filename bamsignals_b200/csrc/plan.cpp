@@ -27,15 +27,28 @@ void resolve_regions(const BamFile& bam, int64_t R, const char* const* seq_level
     }
 }
 
+const std::vector<int64_t>& Regions::sorted_order() const {
+    if (int64_t(order.size()) == R) return order;
+    order.resize(R);
+    std::iota(order.begin(), order.end(), int64_t(0));
+    bool sorted = true;
+    for (int64_t i = 1; i < R && sorted; ++i)
+        sorted = rid[i - 1] < rid[i] || (rid[i - 1] == rid[i] && loc[i - 1] <= loc[i]);
+    if (!sorted) {
+        // sort packed 64-bit keys (rid, loc) with the index as payload: cheaper than an indirect comparator
+        std::vector<std::pair<uint64_t, int64_t>> keyed(R);
+        for (int64_t i = 0; i < R; ++i) keyed[i] = {uint64_t(uint32_t(rid[i])) << 32 | uint32_t(loc[i] ^ int32_t(0x80000000)), i};
+        std::sort(keyed.begin(), keyed.end());
+        for (int64_t i = 0; i < R; ++i) order[i] = keyed[i].second;
+    }
+    return order;
+}
+
 void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int64_t* out_offsets, int tile_ints,
                 HostTiles* t) {
     const int64_t R = rg.R;
     const int mult = ss ? 2 : 1;
-    std::vector<int64_t> order(R);
-    std::iota(order.begin(), order.end(), int64_t(0));
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return rg.rid[a] != rg.rid[b] ? rg.rid[a] < rg.rid[b] : (rg.loc[a] != rg.loc[b] ? rg.loc[a] < rg.loc[b] : a < b);
-    });
+    const std::vector<int64_t>& order = rg.sorted_order();
     auto push = [&](int32_t rid, int64_t loc, int64_t len, int32_t strand, int64_t off, int64_t ints) {
         t->rid.push_back(rid); t->loc.push_back(int32_t(loc)); t->len.push_back(int32_t(len));
         t->strand.push_back(strand); t->out_off.push_back(off);
@@ -104,12 +117,11 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     struct Q { int32_t rid; int64_t beg, end; };
     std::vector<Q> qs;
     qs.reserve(rg.R);
-    for (int64_t i = 0; i < rg.R; ++i) {
+    for (int64_t i : rg.sorted_order()) {                        // (rid, loc) order == (rid, beg) order: ext is constant
         if (rg.width[i] == 0) continue;
         const int64_t b = std::max<int64_t>(0, int64_t(rg.loc[i]) - ext), e = int64_t(rg.loc[i]) + rg.width[i] + ext;
         if (e > b) qs.push_back(Q{rg.rid[i], b, e});
     }
-    std::sort(qs.begin(), qs.end(), [](const Q& a, const Q& b) { return a.rid != b.rid ? a.rid < b.rid : a.beg < b.beg; });
     lap("sort regions");
     std::vector<VRange> ranges;
     for (size_t i = 0; i < qs.size();) {

@@ -14,6 +14,10 @@ struct Regions {            // parseRegions' result (src/bamsignals.cpp:92-135) 
     int64_t R = 0;
     std::vector<int32_t> rid, loc, width;
     std::vector<int8_t> strand;
+    // indices in (rid, loc) order — the std::sort of src/bamsignals.cpp:246; computed once (sorted_order()) and shared
+    // by the tile builder and the fetch planner
+    mutable std::vector<int64_t> order;
+    const std::vector<int64_t>& sorted_order() const;
 };
 
 struct HostTiles {          // one row per counting tile, in (rid, loc) order

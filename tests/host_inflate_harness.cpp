@@ -60,19 +60,59 @@ static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint3
                 run += len[lane];
                 if (valid && !m && !sk) out[pos[lane]] = uint8_t(t[lane]);
             }
-            for (int k = 0; k < 32; ++k) {
-                if (!(base + k < nq) || !(t[k] >> 31)) continue;
-                const uint32_t mlen = t[k] & 0x1ffu, mdist = ((t[k] >> 16) & 0x7fffu) + 1u, mpos = pos[k];
-                const uint32_t K = mdist >= 32 ? mdist : mdist * (31u / mdist + 1u);
-                for (uint32_t s0 = 0; s0 < mlen; s0 += 32) {
-                    uint8_t tmp[32];
-                    for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) {     // all loads of the step ...
-                        const uint32_t j = s0 + lane;
-                        if (s0 == 0) tmp[lane] = (mdist >= 32 || mdist >= mlen) ? out[mpos + j - mdist] : out[mpos - mdist + (j % mdist)];
-                        else tmp[lane] = out[mpos + j - K];
+            // waves, exactly as k_inflate_q2 replays them
+            uint32_t pending = 0;
+            for (int k = 0; k < 32; ++k) if (base + k < nq && (t[k] >> 31)) pending |= 1u << k;
+            while (pending) {
+                const int first = __builtin_ctz(pending);
+                const uint32_t front = pos[first];
+                const uint32_t flen = t[first] & 0x1ffu;
+                if (flen > 32u) {
+                    const uint32_t mlen = flen, mdist = ((t[first] >> 16) & 0x7fffu) + 1u, mpos = front;
+                    const uint32_t K = mdist >= 32 ? mdist : mdist * (31u / mdist + 1u);
+                    for (uint32_t s0 = 0; s0 < mlen; s0 += 32) {
+                        uint8_t tmp[32];
+                        for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) {     // all loads of the step ...
+                            const uint32_t j = s0 + lane;
+                            if (s0 == 0) tmp[lane] = (mdist >= 32 || mdist >= mlen) ? out[mpos + j - mdist] : out[mpos - mdist + (j % mdist)];
+                            else tmp[lane] = out[mpos + j - K];
+                        }
+                        for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) out[mpos + s0 + lane] = tmp[lane];   // ... then all stores
                     }
-                    for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) out[mpos + s0 + lane] = tmp[lane];   // ... then all stores
+                    pending &= ~(1u << first);
+                    continue;
                 }
+                uint32_t ready = 0;
+                for (int k = 0; k < 32; ++k) {
+                    if (!((pending >> k) & 1u)) continue;
+                    const uint32_t ol = t[k] & 0x1ffu, od = ((t[k] >> 16) & 0x7fffu) + 1u;
+                    const uint32_t src_hi = pos[k] < pos[k] - od + ol ? pos[k] : pos[k] - od + ol;
+                    if (ol <= 32u && src_hi <= front) ready |= 1u << k;
+                }
+                // Ready lanes run concurrently on the GPU, so they must not depend on each other: replay them in REVERSE
+                // token order here - a lane that read bytes another ready lane has yet to write would break the CRC.
+                for (int k = 31; k >= 0; --k) {
+                    if (!((ready >> k) & 1u)) continue;
+                    const uint32_t ol = t[k] & 0x1ffu, od = ((t[k] >> 16) & 0x7fffu) + 1u;
+                    for (uint32_t done = 0; done < ol; done += 8) {
+                        const uint32_t n = ol - done < 8 ? ol - done : 8;
+                        uint8_t* d = out + pos[k] + done;
+                        if (pos[k] + done >= 8) {
+                            const uint8_t* sp = d - (od > 8 ? od : 8);
+                            uint64_t w = 0;
+                            for (int q = 0; q < 8; ++q) w |= uint64_t(sp[q]) << (8 * q);
+                            if (od < 8) {
+                                uint64_t rep = w >> (8u * (8u - od));
+                                for (uint32_t filled = od; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
+                                w = rep;
+                            }
+                            for (uint32_t q = 0; q < n; ++q) d[q] = uint8_t(w >> (8 * q));
+                        } else {
+                            for (uint32_t q = 0; q < n; ++q) d[q] = d[int(q) - int(od)];
+                        }
+                    }
+                }
+                pending &= ~ready;
             }
             pos_base += run;
         }

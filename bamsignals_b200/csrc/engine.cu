@@ -6,13 +6,16 @@
 // No CPU fallback: every entry point needs a CUDA device.
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 
 #include "bamio.h"
@@ -34,6 +37,7 @@ constexpr size_t kCompChunk = 16u << 20;        // compressed bytes per pinned u
 constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
+constexpr int kOutSlots = 3;                    // pinned result-staging ring
 
 struct DevBuf {
     void* p = nullptr;
@@ -68,7 +72,7 @@ struct PinBuf {
 struct DeviceCtx {
     int dev = 0;
     bool init = false;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
@@ -77,8 +81,8 @@ struct DeviceCtx {
     DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
     PinBuf h_total;
     cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
-    PinBuf h_scalars, h_out[2], h_tiles;
-    cudaEvent_t ev_d2h[2] = {};
+    PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front;
+    cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {};
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
 
@@ -89,12 +93,15 @@ struct DeviceCtx {
         BSG_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
         for (int i = 0; i < kSlots; ++i) {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < kOutSlots; ++i) BSG_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+        h_front.ensure(64);
         for (int i = 0; i < 2; ++i) {
-            BSG_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_total[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_gfree[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_inflated[i], cudaEventDisableTiming));
@@ -125,8 +132,9 @@ struct DeviceCtx {
         for (auto& b : tab) b.release();
         c0.release(); c1.release(); tiles_i32.release(); tiles_i64.release(); out.release(); scalars.release();
         raw_all.release(); offs_all.release(); batch_table.release(); h_scalars.release();
-        h_out[0].release(); h_out[1].release(); h_tiles.release();
-        cudaEventDestroy(ev_d2h[0]); cudaEventDestroy(ev_d2h[1]);
+        for (int i = 0; i < kOutSlots; ++i) { h_out[i].release(); cudaEventDestroy(ev_d2h[i]); }
+        h_tiles.release(); h_front.release();
+        cudaEventDestroy(ev_front[0]); cudaEventDestroy(ev_front[1]);
         for (int i = 0; i < 2; ++i) {
             g_comp[i].release(); g_raw[i].release(); g_offs[i].release(); g_blocks[i].release(); g_crc[i].release(); g_walkers[i].release();
             g_counts[i].release(); g_base[i].release(); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_gfree[i]);
@@ -136,7 +144,7 @@ struct DeviceCtx {
         g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
-        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux);
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h);
         init = false;
     }
 };
@@ -337,17 +345,20 @@ public:
     void request_prefault(int32_t* out, int64_t total) { prefault_output(out, total); }
     void prefault_output(int32_t* out, int64_t total) {
         if (!out || total < (int64_t(1) << 22)) return;
+        // One atomic `or 0` per page: a write fault that leaves the contents alone, so it may run concurrently with
+        // the scatter of early tiles.  (MADV_POPULATE_WRITE was measured too: it holds the process's mmap lock for
+        // whole ranges and starved the planner's allocations, plan 13 -> 39 ms.)
         const size_t bytes = size_t(total) * 4, piece = size_t(2) << 20;
         const int n = int((bytes + piece - 1) / piece);
         {
             std::lock_guard<std::mutex> g(pf_m_);
             pf_left_ += n;
         }
-        volatile uint8_t* base = reinterpret_cast<volatile uint8_t*>(out);
+        uint8_t* base = reinterpret_cast<uint8_t*>(out);
         for (int k = 0; k < n; ++k)
             pool_->submit_low([this, base, bytes, piece, k](int) {
                 const size_t lo = size_t(k) * piece, hi = std::min(bytes, lo + piece);
-                for (size_t o = lo; o < hi; o += 4096) base[o] = 0;
+                for (size_t o = lo; o < hi; o += 4096) __atomic_fetch_or(base + o, uint8_t(0), __ATOMIC_RELAXED);
                 std::lock_guard<std::mutex> g(pf_m_);
                 if (--pf_left_ == 0) pf_cv_.notify_all();
             });
@@ -356,7 +367,7 @@ public:
         std::unique_lock<std::mutex> lk(pf_m_);
         pf_cv_.wait(lk, [&] { return pf_left_ == 0; });
     }
-    ~Session() { wait_prefault(); }
+    ~Session() { stop_streamer(true); wait_prefault(); }
 
     // Tiles depend only on the regions and on (mode, binsize, ss, layout): build + upload them before any device
     // work of the call is queued, and keep them for the next call of a staged session.
@@ -367,7 +378,8 @@ public:
         if (tiles_valid_ && tiles_mode_ == mode && tiles_binsize_ == binsize && tiles_ss_ == ss &&
             tiles_offsets_.size() == size_t(R + 1) && memcmp(tiles_offsets_.data(), out_offsets, size_t(R + 1) * 8) == 0)
             return;
-        HostTiles ht;
+        HostTiles& ht = ht_;
+        ht = HostTiles();
         // Tile size: as large as shared memory allows (fewer halo re-reads), but small enough that the launch has
         // >= ~16 CTAs per SM: a few huge regions (C4: 24 whole chromosomes) must still fill 148 SMs.
         const int64_t total_ints = out_offsets[R];
@@ -375,6 +387,10 @@ public:
         while (tile_ints > 512 && total_ints / tile_ints < 148 * 16) tile_ints >>= 1;
         make_tiles(rg_, mode, binsize, ss, out_offsets, tile_ints, &ht);
         const int64_t nt = ht.size();
+        // The device result buffer is laid out in TILE order (tile t at dev_off[t]): a run of consecutive tiles is one
+        // contiguous D2H copy, whatever order the caller's regions came in; the host scatters tiles to the caller.
+        tile_dev_off_.assign(size_t(nt) + 1, 0);
+        for (int64_t t = 0; t < nt; ++t) tile_dev_off_[t + 1] = tile_dev_off_[t] + ht.ints[t];
         c.tiles_i32.ensure(size_t(nt) * 4 * sizeof(int32_t) + 64);
         c.tiles_i64.ensure(size_t(nt) * 3 * sizeof(int64_t) + 64);
         int32_t* ti = c.tiles_i32.as<int32_t>();
@@ -384,7 +400,7 @@ public:
             uint8_t* h = c.h_tiles.as<uint8_t>();
             memcpy(h, ht.rid.data(), nt * 4); memcpy(h + nt * 4, ht.loc.data(), nt * 4);
             memcpy(h + nt * 8, ht.len.data(), nt * 4); memcpy(h + nt * 12, ht.strand.data(), nt * 4);
-            memcpy(h + nt * 16, ht.out_off.data(), nt * 8);
+            memcpy(h + nt * 16, tile_dev_off_.data(), nt * 8);
             BSG_CUDA(cudaMemcpyAsync(ti, h, nt * 16, cudaMemcpyHostToDevice, c.s_comp));
             BSG_CUDA(cudaMemcpyAsync(tl, h + nt * 16, nt * 8, cudaMemcpyHostToDevice, c.s_comp));
             BSG_CUDA(cudaStreamSynchronize(c.s_comp));   // h_tiles is reused by the next call
@@ -396,86 +412,59 @@ public:
         tiles_valid_ = true;
     }
 
-    void count(Mode mode, const FilterParams& fp, int32_t binsize, int ss, int32_t* out, const int64_t* out_offsets,
-               int32_t* const* out_ptrs, bool want_output) {
+    // ---- counting: begin_count() / advance() / finish_count() ---------------------------------------------------------
+    // The reference finishes a region as soon as the sorted read stream has passed its end + ext
+    // (src/bamsignals.cpp:278); the same observation lets the result leave the device while later batches are still
+    // being inflated: a tile is final once the last decoded record's (tid, pos) is >= (rid, end + ext).
+    void begin_count(Mode mode, const FilterParams& fp, int32_t binsize, int ss, int64_t ext, int32_t* out,
+                     const int64_t* out_offsets, int32_t* const* out_ptrs, bool want_output) {
         DeviceCtx& c = *ctx_;
         const int64_t R = rg_.R;
+        stop_streamer(true);                         // left over from a call that failed half-way (staged sessions persist)
         prepare_tiles(mode, binsize, ss, out_offsets);
+        cnt_ = CountState();
+        cnt_.active = true; cnt_.mode = mode; cnt_.fp = fp; cnt_.binsize = binsize; cnt_.ss = ss;
+        cnt_.out = out; cnt_.out_offsets = out_offsets; cnt_.out_ptrs = out_ptrs;
         const int64_t total = out_offsets[R];
-        const int64_t nt = n_tiles_;
-        tm_.n_tiles = nt;
+        cnt_.want_output = want_output && total > 0;
+        if (cnt_.want_output && !out && !out_ptrs) fail(BSG_EARG, "either out or out_ptrs must be given");
+        tm_.n_tiles = n_tiles_;
         tm_.out_elems = total;
         c.out.ensure(size_t(total) * sizeof(int32_t) + 64);
-        int32_t* ti = c.tiles_i32.as<int32_t>();
-        int64_t* tl = c.tiles_i64.as<int64_t>();
-        TileTable tt{ti, ti + nt, ti + 2 * nt, ti + 3 * nt, tl, tl + nt, tl + 2 * nt};
+        // (rid, end + ext) as one key, prefix-maxed over the tile order: tiles [0, t) are final iff final_key[t-1] <= frontier
+        tile_final_key_.resize(size_t(n_tiles_));
+        uint64_t run = 0;
+        for (int64_t t = 0; t < n_tiles_; ++t) {
+            const int64_t e = std::min<int64_t>(int64_t(ht_.loc[t]) + ht_.len[t] + ext, INT32_MAX);
+            run = std::max(run, uint64_t(uint32_t(ht_.rid[t])) << 32 | uint64_t(uint32_t(std::max<int64_t>(e, 0))));
+            tile_final_key_[t] = run;
+        }
+        if (cnt_.want_output) start_streamer();
+    }
+
+    // Rows [0, rows) of the read table are decoded and `frontier` = (tid, pos) of the last of them: filter the new rows
+    // and count + ship every tile that can no longer change.
+    void advance(int64_t rows, uint32_t f_tid, int32_t f_pos) {
+        if (!cnt_.active) return;
+        filter_rows(rows);
+        const uint64_t key = uint64_t(f_tid) << 32 | uint64_t(uint32_t(std::max(f_pos, 0)));
+        const int64_t t_new = std::upper_bound(tile_final_key_.begin(), tile_final_key_.end(), key) - tile_final_key_.begin();
+        // worth a launch + copy only in decent portions
+        if (t_new > cnt_.t_done && tile_dev_off_[t_new] - tile_dev_off_[cnt_.t_done] >= (int64_t(4) << 20)) count_tiles(cnt_.t_done, t_new);
+    }
+
+    void finish_count() {
+        DeviceCtx& c = *ctx_;
+        filter_rows(n_rows_);
+        if (n_tiles_ > cnt_.t_done) count_tiles(cnt_.t_done, n_tiles_);
         DeviceScalars* sc = c.scalars.as<DeviceScalars>();
-        ReadTable t = table();
-        int32_t* c0 = c.c0.as<int32_t>();
-        int32_t* c1 = c.c1.as<int32_t>();
-        {
-            Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            if (mode == MODE_COVERAGE) launch_filter_coverage(t, n_rows_, fp, c0, c1, sc, c.s_comp);
-            else launch_filter_pileup(t, n_rows_, fp, c0, c1, sc, c.s_comp);
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
-            kt_.filter.push_back(sp); kt_.launches += n_rows_ > 0;
-        }
-        {
-            Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            launch_join(t, n_rows_, tt, nt, sc, c.s_comp);
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
-            kt_.join.push_back(sp); kt_.launches += nt > 0;
-        }
-        {
-            Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            if (mode == MODE_COUNT) launch_count(tt, nt, c0, c1, ss, c.out.as<int32_t>(), sc, c.s_comp);
-            else if (mode == MODE_PROFILE) launch_profile(tt, nt, c0, c1, ss, binsize, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
-            else launch_coverage(tt, nt, c0, c1, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
-            kt_.count.push_back(sp); kt_.launches += nt > 0;
-        }
         BSG_CUDA(cudaGetLastError());
         BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
-
-        // result: device -> pinned ring -> caller memory (copies of chunk k+1 overlap the host scatter of chunk k)
-        wait_prefault();
         const double t_d2h = now_ms();
-        if (want_output && total > 0) {
-            if (!out && !out_ptrs) fail(BSG_EARG, "either out or out_ptrs must be given");
-            const int64_t chunk = kD2HChunk / 4;
-            for (int k = 0; k < 2; ++k) c.h_out[k].ensure(size_t(std::min<int64_t>(chunk, total)) * 4);
-            const int64_t nchunks = (total + chunk - 1) / chunk;
-            auto scatter = [&](int64_t k) {
-                const int64_t lo = k * chunk, hi = std::min(total, lo + chunk);
-                BSG_CUDA(cudaEventSynchronize(c.ev_d2h[k & 1]));
-                const int32_t* src = c.h_out[k & 1].as<int32_t>();
-                const int64_t grain = 1 << 18;   // 1 MiB per task
-                pool_->parallel_for(hi - lo, grain, [&](int64_t a, int64_t b, int) {
-                    if (out) { memcpy(out + lo + a, src + a, size_t(b - a) * 4); return; }
-                    int64_t pos = lo + a;
-                    const int64_t end = lo + b;
-                    int64_t r = std::upper_bound(out_offsets, out_offsets + R + 1, pos) - out_offsets - 1;
-                    while (pos < end && r < R) {
-                        const int64_t stop = std::min(end, out_offsets[r + 1]);
-                        if (stop > pos && out_ptrs[r]) memcpy(out_ptrs[r] + (pos - out_offsets[r]), src + (pos - lo), size_t(stop - pos) * 4);
-                        pos = std::max(pos, stop);
-                        ++r;
-                    }
-                });
-            };
-            for (int64_t k = 0; k < nchunks; ++k) {
-                const int64_t lo = k * chunk, hi = std::min(total, lo + chunk);
-                BSG_CUDA(cudaMemcpyAsync(c.h_out[k & 1].p, c.out.as<int32_t>() + lo, size_t(hi - lo) * 4, cudaMemcpyDeviceToHost, c.s_comp));
-                BSG_CUDA(cudaEventRecord(c.ev_d2h[k & 1], c.s_comp));
-                if (k > 0) scatter(k - 1);
-            }
-            scatter(nchunks - 1);
-        }
+        stop_streamer(false);
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         tm_.ms_d2h = now_ms() - t_d2h;
+        cnt_.active = false;
         const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
         check_status(hs->status);
         tm_.records = n_rows_;
@@ -483,6 +472,152 @@ public:
         tm_.candidates = int64_t(hs->candidates);
     }
 
+    void count(Mode mode, const FilterParams& fp, int32_t binsize, int ss, int32_t* out, const int64_t* out_offsets,
+               int32_t* const* out_ptrs, bool want_output) {
+        begin_count(mode, fp, binsize, ss, 0, out, out_offsets, out_ptrs, want_output);
+        finish_count();
+    }
+
+private:
+    struct CountState {
+        bool active = false, want_output = false;
+        Mode mode = MODE_COUNT;
+        FilterParams fp{};
+        int32_t binsize = 1;
+        int ss = 0;
+        int32_t* out = nullptr;
+        const int64_t* out_offsets = nullptr;
+        int32_t* const* out_ptrs = nullptr;
+        int64_t rows_filtered = 0, t_done = 0;
+    };
+    struct OutJob { int slot; int64_t t0, t1; cudaEvent_t computed; };
+
+    void filter_rows(int64_t rows) {
+        DeviceCtx& c = *ctx_;
+        if (rows <= cnt_.rows_filtered) return;
+        Span sp{c.timing_event(), c.timing_event()};
+        BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+        if (cnt_.mode == MODE_COVERAGE) launch_filter_coverage(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), c.s_comp);
+        else launch_filter_pileup(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), c.s_comp);
+        BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+        kt_.filter.push_back(sp); kt_.launches += 1;
+        cnt_.rows_filtered = rows;
+    }
+
+    // K3 + K4/K5 for tiles [t0, t1) over the rows filtered so far, then hand them to the output streamer
+    void count_tiles(int64_t t0, int64_t t1) {
+        DeviceCtx& c = *ctx_;
+        const int64_t nt_all = n_tiles_, n = t1 - t0;
+        int32_t* ti = c.tiles_i32.as<int32_t>();
+        int64_t* tl = c.tiles_i64.as<int64_t>();
+        TileTable tt{ti + t0, ti + nt_all + t0, ti + 2 * nt_all + t0, ti + 3 * nt_all + t0, tl + t0, tl + nt_all + t0, tl + 2 * nt_all + t0};
+        DeviceScalars* sc = c.scalars.as<DeviceScalars>();
+        int32_t* c0 = c.c0.as<int32_t>();
+        int32_t* c1 = c.c1.as<int32_t>();
+        {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            launch_join(table(), cnt_.rows_filtered, tt, n, sc, c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.join.push_back(sp); kt_.launches += 1;
+        }
+        {
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            if (cnt_.mode == MODE_COUNT) launch_count(tt, n, c0, c1, cnt_.ss, c.out.as<int32_t>(), sc, c.s_comp);
+            else if (cnt_.mode == MODE_PROFILE) launch_profile(tt, n, c0, c1, cnt_.ss, cnt_.binsize, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
+            else launch_coverage(tt, n, c0, c1, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            kt_.count.push_back(sp); kt_.launches += 1;
+            if (cnt_.want_output) ship_tiles(t0, t1, sp.b);
+        }
+        cnt_.t_done = t1;
+    }
+
+    // ---- output streamer: D2H on its own stream into a pinned ring, a host thread scatters tiles to the caller ------------
+    void start_streamer() {
+        DeviceCtx& c = *ctx_;
+        for (int k = 0; k < kOutSlots; ++k) c.h_out[k].ensure(size_t(kD2HChunk));
+        os_stop_ = false; os_abort_ = false;
+        os_jobs_.clear();
+        os_err_ = Error{0, ""};
+        os_thread_ = std::thread([this] { streamer_main(); });
+    }
+    // main thread: never blocks here, the streamer thread does the copies
+    void ship_tiles(int64_t t0, int64_t t1, cudaEvent_t computed) {
+        {
+            std::lock_guard<std::mutex> g(os_m_);
+            os_jobs_.push_back(OutJob{0, t0, t1, computed});
+        }
+        os_cv_.notify_all();
+    }
+    void streamer_main() {
+        DeviceCtx& c = *ctx_;
+        cudaSetDevice(c.dev);
+        const int64_t cap = kD2HChunk / 4;
+        for (;;) {
+            OutJob job;
+            {
+                std::unique_lock<std::mutex> lk(os_m_);
+                os_cv_.wait(lk, [&] { return os_stop_ || !os_jobs_.empty(); });
+                if (os_jobs_.empty()) return;
+                job = os_jobs_.front();
+                os_jobs_.pop_front();
+            }
+            if (os_abort_ || os_err_.code) continue;
+            // pieces of <= 32 MiB at tile boundaries; the copy of piece k+1 is in flight while piece k is scattered
+            std::vector<int64_t> cut{job.t0};
+            for (int64_t p0 = job.t0; p0 < job.t1;) {
+                int64_t p1 = p0 + 1;
+                while (p1 < job.t1 && tile_dev_off_[p1 + 1] - tile_dev_off_[p0] <= cap) ++p1;
+                cut.push_back(p1);
+                p0 = p1;
+            }
+            const int np = int(cut.size()) - 1;
+            cudaError_t e = cudaStreamWaitEvent(c.s_d2h, job.computed, 0);
+            auto issue = [&](int k) {
+                const int slot = k % kOutSlots;
+                const int64_t ints = tile_dev_off_[cut[k + 1]] - tile_dev_off_[cut[k]];
+                cudaError_t r = cudaMemcpyAsync(c.h_out[slot].p, c.out.as<int32_t>() + tile_dev_off_[cut[k]], size_t(ints) * 4, cudaMemcpyDeviceToHost, c.s_d2h);
+                if (r == cudaSuccess) r = cudaEventRecord(c.ev_d2h[slot], c.s_d2h);
+                return r;
+            };
+            for (int k = 0; k < np && k < kOutSlots - 1 && e == cudaSuccess; ++k) e = issue(k);
+            for (int k = 0; k < np && e == cudaSuccess; ++k) {
+                if (k + kOutSlots - 1 < np) e = issue(k + kOutSlots - 1);      // its slot was scattered in iteration k-1
+                if (e != cudaSuccess) break;
+                e = cudaEventSynchronize(c.ev_d2h[k % kOutSlots]);
+                if (e != cudaSuccess) break;
+                const int32_t* src = c.h_out[k % kOutSlots].as<int32_t>();
+                const int64_t t_lo = cut[k], base = tile_dev_off_[t_lo], n = cut[k + 1] - t_lo;
+                const int64_t grain = std::max<int64_t>(1, n / (int64_t(pool_->size()) * 4));
+                pool_->parallel_for(n, grain, [&](int64_t a, int64_t b, int) {
+                    for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
+                        int32_t* dst = cnt_.out ? cnt_.out + ht_.out_off[t]
+                                                : (cnt_.out_ptrs[ht_.region[t]] ? cnt_.out_ptrs[ht_.region[t]] + (ht_.out_off[t] - cnt_.out_offsets[ht_.region[t]]) : nullptr);
+                        if (dst) memcpy(dst, src + (tile_dev_off_[t] - base), size_t(ht_.ints[t]) * 4);
+                    }
+                });
+            }
+            if (e != cudaSuccess) {
+                std::lock_guard<std::mutex> g(os_m_);
+                if (!os_err_.code) os_err_ = Error{BSG_ECUDA, std::string("CUDA error in result copy: ") + cudaGetErrorString(e)};
+            }
+        }
+    }
+    void stop_streamer(bool abort) {
+        if (!os_thread_.joinable()) return;
+        {
+            std::lock_guard<std::mutex> g(os_m_);
+            os_stop_ = true;
+            if (abort) os_abort_ = true;
+        }
+        os_cv_.notify_all();
+        os_thread_.join();
+        if (!abort && os_err_.code) throw os_err_;
+    }
+
+public:
     void check_status(uint32_t status) {
         if (status & STATUS_BAD_CRC) fail(BSG_EFORMAT, "BGZF CRC32 mismatch in " + bam_.path());
         if (status & STATUS_BAD_DEFLATE) fail(BSG_EFORMAT, "BGZF inflate failed (corrupt DEFLATE stream or ISIZE mismatch) in " + bam_.path());
@@ -497,7 +632,8 @@ public:
         tm_.ms_count = sum_ms(kt_.count);
         tm_.ms_kernels = tm_.ms_decode + tm_.ms_filter + tm_.ms_join + tm_.ms_count;
         if (!kt_.count.empty()) {
-            const cudaEvent_t first = kt_.decode.empty() ? kt_.filter.front().a : kt_.decode.front().a;
+            const cudaEvent_t first = !kt_.decode.empty() ? kt_.decode.front().a
+                                    : (!kt_.filter.empty() ? kt_.filter.front().a : kt_.join.front().a);
             float ms = 0;
             cudaEventElapsedTime(&ms, first, kt_.count.back().b);
             tm_.ms_device = ms;
@@ -692,6 +828,7 @@ private:
         uint64_t raw_base = 0; int64_t offs_base = 0;
         struct Pending { bool valid = false; int slot = 0; uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0; };
         Pending pend;
+        bool front_valid = false; int front_slot = 0; int64_t front_rows = 0;
         std::vector<Span> inflate_spans, walk_spans;
         auto finish = [&](Pending& p) {
             if (!p.valid) return;
@@ -703,9 +840,26 @@ private:
             } else {
                 Span sp{c.timing_event(), c.timing_event()};
                 BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+                // the previous batch's frontier has arrived by now: count + ship every tile it finalises
+                if (front_valid) {
+                    BSG_CUDA(cudaEventSynchronize(c.ev_front[front_slot]));
+                    const int32_t* f = c.h_front.as<int32_t>() + 2 * front_slot;
+                    advance(front_rows, uint32_t(f[0]), f[1]);
+                    front_valid = false;
+                }
                 launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_comp);
                 BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
+                if (n > 0 && cnt_.active) {
+                    // (tid, pos) of the last decoded record -> pinned, consumed one batch later
+                    ReadTable t = table();
+                    front_slot ^= 1;
+                    int32_t* f = c.h_front.as<int32_t>() + 2 * front_slot;
+                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_comp));
+                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_comp));
+                    BSG_CUDA(cudaEventRecord(c.ev_front[front_slot], c.s_comp));
+                    front_valid = true; front_rows = n_rows_ + n;
+                }
             }
             if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_crc[p.slot], 0));
             BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], c.s_comp));
@@ -906,6 +1060,18 @@ private:
     std::mutex pf_m_;
     std::condition_variable pf_cv_;
     int pf_left_ = 0;
+    // counting state + output streamer
+    CountState cnt_;
+    HostTiles ht_;
+    std::vector<int64_t> tile_dev_off_;
+    std::vector<uint64_t> tile_final_key_;
+    std::thread os_thread_;
+    std::mutex os_m_;
+    std::condition_variable os_cv_;
+    std::deque<OutJob> os_jobs_;
+    bool os_stop_ = false;
+    std::atomic<bool> os_abort_{false};
+    Error os_err_{0, ""};
     // cached tiles
     bool tiles_valid_ = false;
     Mode tiles_mode_ = MODE_COUNT;
@@ -1004,8 +1170,9 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
                 }
                 Session s(bam, std::move(sub), o, o.devices[d]);
                 s.prepare_tiles(mode, binsize, ss, loff.data());
+                s.begin_count(mode, fp, binsize, ss, ext, nullptr, loff.data(), lptr.data(), true);
                 s.stage(ext, false);
-                s.count(mode, fp, binsize, ss, nullptr, loff.data(), lptr.data(), true);
+                s.finish_count();
                 s.finish_timings(t0);
                 tms[d] = s.timings();
             } catch (Error& e) { errs[d] = e; }
@@ -1088,9 +1255,10 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
         const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
         s.prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
         if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
-        s.stage(ext, false);
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
-        s.count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, out, out_offsets, out_ptrs, true);
+        s.begin_count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, ext, out, out_offsets, out_ptrs, true);
+        s.stage(ext, false);
+        s.finish_count();
         s.finish_timings(t0);
     });
 }
@@ -1112,9 +1280,11 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         s.prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
         if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
-        s.stage(ext_coverage(tlen_filter, tspan), false);
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
-        s.count(MODE_COVERAGE, fp, 1, 0, out, out_offsets, out_ptrs, true);
+        const int64_t ext = ext_coverage(tlen_filter, tspan);
+        s.begin_count(MODE_COVERAGE, fp, 1, 0, ext, out, out_offsets, out_ptrs, true);
+        s.stage(ext, false);
+        s.finish_count();
         s.finish_timings(t0);
     });
 }

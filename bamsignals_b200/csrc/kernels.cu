@@ -194,9 +194,10 @@ __device__ __forceinline__ bool keep_read(const FilterParams& p, uint32_t fm, in
 template <bool COVERAGE>
 __global__ void __launch_bounds__(kThreads) k_filter(const int4* __restrict__ pos4, const int4* __restrict__ end4,
                                                      const int4* __restrict__ tlen4, const uint4* __restrict__ fm4,
-                                                     int64_t n, FilterParams p, int4* __restrict__ c0v,
+                                                     int64_t row_lo, int64_t n, FilterParams p, int4* __restrict__ c0v,
                                                      int4* __restrict__ c1v, DeviceScalars* sc) {
-    const int64_t q = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+    // rows [row_lo, n); the first quad may start below row_lo: those rows are recomputed (same values) but not counted
+    const int64_t q = (row_lo >> 2) + int64_t(blockIdx.x) * kThreads + threadIdx.x;
     const int64_t n4 = (n + 3) >> 2;
     int hlo = INT_MIN, hhi = INT_MIN, kept = 0;
     if (q < n4) {
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_filter(const int4* __restrict__ po
                 o1[j] = keep ? e : INT_MIN;
                 if (keep) { hlo = max(hlo, e - ps[j]); hhi = max(hhi, ps[j] - s); }
             }
-            kept += keep;
+            kept += keep && (4 * q + j >= row_lo);
         }
         c0v[q] = make_int4(o0[0], o0[1], o0[2], o0[3]);
         c1v[q] = make_int4(o1[0], o1[1], o1[2], o1[3]);
@@ -488,18 +489,18 @@ void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_ch
     k_decode<<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, sc);
 }
 
-void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
-    if (n <= 0) return;
-    const int64_t n4 = (n + 3) / 4, grid = (n4 + kThreads - 1) / kThreads;
+void launch_filter_pileup(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
+    if (n <= row_lo) return;
+    const int64_t n4 = (n + 3) / 4 - (row_lo >> 2), grid = (n4 + kThreads - 1) / kThreads;
     k_filter<false><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
-                                                        (const uint4*)t.flagmq, n, p, (int4*)c0, (int4*)c1, sc);
+                                                        (const uint4*)t.flagmq, row_lo, n, p, (int4*)c0, (int4*)c1, sc);
 }
 
-void launch_filter_coverage(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
-    if (n <= 0) return;
-    const int64_t n4 = (n + 3) / 4, grid = (n4 + kThreads - 1) / kThreads;
+void launch_filter_coverage(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
+    if (n <= row_lo) return;
+    const int64_t n4 = (n + 3) / 4 - (row_lo >> 2), grid = (n4 + kThreads - 1) / kThreads;
     k_filter<true><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
-                                                       (const uint4*)t.flagmq, n, p, (int4*)c0, (int4*)c1, sc);
+                                                       (const uint4*)t.flagmq, row_lo, n, p, (int4*)c0, (int4*)c1, sc);
 }
 
 void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s) {

@@ -89,9 +89,9 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
                  uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
 
-// K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415).
-void launch_filter_pileup(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
-void launch_filter_coverage(ReadTable t, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
+// K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415) for table rows [row_lo, n).
+void launch_filter_pileup(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
+void launch_filter_coverage(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
 
 // K3: per tile, binary-search the (tid,pos)-sorted table for the candidate row range (the job of the sort + chunk
 // + sweep in overlapAndPileup, src/bamsignals.cpp:246-285).

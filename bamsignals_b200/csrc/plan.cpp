@@ -49,13 +49,16 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
     const int64_t R = rg.R;
     const int mult = ss ? 2 : 1;
     const std::vector<int64_t>& order = rg.sorted_order();
+    int64_t cur_region = 0;
     auto push = [&](int32_t rid, int64_t loc, int64_t len, int32_t strand, int64_t off, int64_t ints) {
         t->rid.push_back(rid); t->loc.push_back(int32_t(loc)); t->len.push_back(int32_t(len));
         t->strand.push_back(strand); t->out_off.push_back(off);
+        t->region.push_back(cur_region); t->ints.push_back(int32_t(ints));
         t->max_tile_ints = std::max<int64_t>(t->max_tile_ints, ints);
     };
     for (int64_t oi = 0; oi < R; ++oi) {
         const int64_t i = order[oi];
+        cur_region = i;
         const int64_t loc = rg.loc[i], width = rg.width[i], base = out_offsets[i];
         const int32_t strand = rg.strand[i];
         if (mode == MODE_COUNT) { push(rg.rid[i], loc, width, strand, base, mult); continue; }

@@ -22,7 +22,9 @@ struct Regions {            // parseRegions' result (src/bamsignals.cpp:92-135) 
 
 struct HostTiles {          // one row per counting tile, in (rid, loc) order
     std::vector<int32_t> rid, loc, len, strand;
-    std::vector<int64_t> out_off;
+    std::vector<int64_t> out_off;      // offset of the tile's ints in the CALLER's flat layout (bsg_output_layout order)
+    std::vector<int64_t> region;       // index of the region the tile belongs to
+    std::vector<int32_t> ints;         // output ints the tile owns
     int max_tile_ints = 0;  // largest number of output ints any tile owns
     int64_t size() const { return int64_t(rid.size()); }
 };

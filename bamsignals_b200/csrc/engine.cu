@@ -72,7 +72,7 @@ struct PinBuf {
 struct DeviceCtx {
     int dev = 0;
     bool init = false;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr, s_hi = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
@@ -82,7 +82,7 @@ struct DeviceCtx {
     PinBuf h_total;
     cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
     PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front;
-    cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {};
+    cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {}, ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
 
@@ -94,6 +94,12 @@ struct DeviceCtx {
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+        {   // decode + count kernels of finished batches overtake the inflate of the next one
+            int lo_p = 0, hi_p = 0;
+            BSG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            BSG_CUDA(cudaStreamCreateWithPriority(&s_hi, cudaStreamNonBlocking, hi_p));
+        }
+        BSG_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
         for (int i = 0; i < kSlots; ++i) {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
@@ -144,7 +150,7 @@ struct DeviceCtx {
         g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
-        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h);
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
         init = false;
     }
 };
@@ -459,10 +465,12 @@ public:
         if (n_tiles_ > cnt_.t_done) count_tiles(cnt_.t_done, n_tiles_);
         DeviceScalars* sc = c.scalars.as<DeviceScalars>();
         BSG_CUDA(cudaGetLastError());
-        BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
+        BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, cnt_stream()));
         const double t_d2h = now_ms();
         stop_streamer(false);
+        BSG_CUDA(cudaStreamSynchronize(cnt_stream()));
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        hi_prio_ = false;
         tm_.ms_d2h = now_ms() - t_d2h;
         cnt_.active = false;
         const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
@@ -492,14 +500,17 @@ private:
     };
     struct OutJob { int slot; int64_t t0, t1; cudaEvent_t computed; };
 
+    cudaStream_t cnt_stream() const { return hi_prio_ ? ctx_->s_hi : ctx_->s_comp; }
+
     void filter_rows(int64_t rows) {
         DeviceCtx& c = *ctx_;
         if (rows <= cnt_.rows_filtered) return;
+        cudaStream_t st = cnt_stream();
         Span sp{c.timing_event(), c.timing_event()};
-        BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-        if (cnt_.mode == MODE_COVERAGE) launch_filter_coverage(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), c.s_comp);
-        else launch_filter_pileup(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), c.s_comp);
-        BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+        BSG_CUDA(cudaEventRecord(sp.a, st));
+        if (cnt_.mode == MODE_COVERAGE) launch_filter_coverage(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), st);
+        else launch_filter_pileup(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), st);
+        BSG_CUDA(cudaEventRecord(sp.b, st));
         kt_.filter.push_back(sp); kt_.launches += 1;
         cnt_.rows_filtered = rows;
     }
@@ -507,6 +518,7 @@ private:
     // K3 + K4/K5 for tiles [t0, t1) over the rows filtered so far, then hand them to the output streamer
     void count_tiles(int64_t t0, int64_t t1) {
         DeviceCtx& c = *ctx_;
+        cudaStream_t st = cnt_stream();
         const int64_t nt_all = n_tiles_, n = t1 - t0;
         int32_t* ti = c.tiles_i32.as<int32_t>();
         int64_t* tl = c.tiles_i64.as<int64_t>();
@@ -516,18 +528,18 @@ private:
         int32_t* c1 = c.c1.as<int32_t>();
         {
             Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            launch_join(table(), cnt_.rows_filtered, tt, n, sc, c.s_comp);
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            BSG_CUDA(cudaEventRecord(sp.a, st));
+            launch_join(table(), cnt_.rows_filtered, tt, n, sc, st);
+            BSG_CUDA(cudaEventRecord(sp.b, st));
             kt_.join.push_back(sp); kt_.launches += 1;
         }
         {
             Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            if (cnt_.mode == MODE_COUNT) launch_count(tt, n, c0, c1, cnt_.ss, c.out.as<int32_t>(), sc, c.s_comp);
-            else if (cnt_.mode == MODE_PROFILE) launch_profile(tt, n, c0, c1, cnt_.ss, cnt_.binsize, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
-            else launch_coverage(tt, n, c0, c1, max_tile_ints_, c.out.as<int32_t>(), sc, c.s_comp);
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            BSG_CUDA(cudaEventRecord(sp.a, st));
+            if (cnt_.mode == MODE_COUNT) launch_count(tt, n, c0, c1, cnt_.ss, c.out.as<int32_t>(), sc, st);
+            else if (cnt_.mode == MODE_PROFILE) launch_profile(tt, n, c0, c1, cnt_.ss, cnt_.binsize, max_tile_ints_, c.out.as<int32_t>(), sc, st);
+            else launch_coverage(tt, n, c0, c1, max_tile_ints_, c.out.as<int32_t>(), sc, st);
+            BSG_CUDA(cudaEventRecord(sp.b, st));
             kt_.count.push_back(sp); kt_.launches += 1;
             if (cnt_.want_output) ship_tiles(t0, t1, sp.b);
         }
@@ -828,7 +840,10 @@ private:
         uint64_t raw_base = 0; int64_t offs_base = 0;
         struct Pending { bool valid = false; int slot = 0; uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0; };
         Pending pend;
-        bool front_valid = false; int front_slot = 0; int64_t front_rows = 0;
+        // the high-priority stream starts behind everything already queued on the compute stream (scalars reset, tiles)
+        hi_prio_ = !keep_raw_;
+        BSG_CUDA(cudaEventRecord(c.ev_order, c.s_comp));
+        BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_order, 0));
         std::vector<Span> inflate_spans, walk_spans;
         auto finish = [&](Pending& p) {
             if (!p.valid) return;
@@ -838,31 +853,29 @@ private:
             if (keep_raw_) {
                 resident_.push_back(ResidentBatch{p.raw_base, p.offs_base, n});
             } else {
+                // decode on the high-priority stream as soon as the walk of this batch is done (ev_total): it overtakes
+                // the inflate of the next batch, which is already queued on the compute stream
+                BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_total[p.slot], 0));
                 Span sp{c.timing_event(), c.timing_event()};
-                BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-                // the previous batch's frontier has arrived by now: count + ship every tile it finalises
-                if (front_valid) {
-                    BSG_CUDA(cudaEventSynchronize(c.ev_front[front_slot]));
-                    const int32_t* f = c.h_front.as<int32_t>() + 2 * front_slot;
-                    advance(front_rows, uint32_t(f[0]), f[1]);
-                    front_valid = false;
-                }
-                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_comp);
-                BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+                BSG_CUDA(cudaEventRecord(sp.a, c.s_hi));
+                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_hi);
+                BSG_CUDA(cudaEventRecord(sp.b, c.s_hi));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
                 if (n > 0 && cnt_.active) {
-                    // (tid, pos) of the last decoded record -> pinned, consumed one batch later
+                    // (tid, pos) of the last decoded record = how far the sorted read stream has come: count + ship
+                    // every tile it finalises while the next batch inflates
                     ReadTable t = table();
-                    front_slot ^= 1;
-                    int32_t* f = c.h_front.as<int32_t>() + 2 * front_slot;
-                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_comp));
-                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_comp));
-                    BSG_CUDA(cudaEventRecord(c.ev_front[front_slot], c.s_comp));
-                    front_valid = true; front_rows = n_rows_ + n;
+                    int32_t* f = c.h_front.as<int32_t>();
+                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
+                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
+                    BSG_CUDA(cudaEventRecord(c.ev_front[0], c.s_hi));
+                    BSG_CUDA(cudaEventSynchronize(c.ev_front[0]));
+                    advance(n_rows_ + n, uint32_t(f[0]), f[1]);
                 }
             }
-            if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_crc[p.slot], 0));
-            BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], c.s_comp));
+            cudaStream_t fs = keep_raw_ ? c.s_comp : c.s_hi;
+            if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(fs, c.ev_crc[p.slot], 0));
+            BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], fs));
             n_rows_ += n;
             p.valid = false;
         };
@@ -1011,6 +1024,7 @@ private:
         }
         finish(pend);
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        BSG_CUDA(cudaStreamSynchronize(c.s_hi));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
         tm_.ms_h2d = t_copy;
         if (getenv("BSG_DEBUG"))
@@ -1062,6 +1076,7 @@ private:
     int pf_left_ = 0;
     // counting state + output streamer
     CountState cnt_;
+    bool hi_prio_ = false;           // decode/count kernels of this call go to the high-priority stream
     HostTiles ht_;
     std::vector<int64_t> tile_dev_off_;
     std::vector<uint64_t> tile_final_key_;

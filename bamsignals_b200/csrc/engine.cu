@@ -456,7 +456,9 @@ public:
         const uint64_t key = uint64_t(f_tid) << 32 | uint64_t(uint32_t(std::max(f_pos, 0)));
         const int64_t t_new = std::upper_bound(tile_final_key_.begin(), tile_final_key_.end(), key) - tile_final_key_.begin();
         // worth a launch + copy only in decent portions
-        if (t_new > cnt_.t_done && tile_dev_off_[t_new] - tile_dev_off_[cnt_.t_done] >= (int64_t(4) << 20)) count_tiles(cnt_.t_done, t_new);
+        if (opts_.stream_min_ints < 0) return;
+        const int64_t min_ints = opts_.stream_min_ints > 0 ? opts_.stream_min_ints : (int64_t(4) << 20);
+        if (t_new > cnt_.t_done && tile_dev_off_[t_new] - tile_dev_off_[cnt_.t_done] >= min_ints) count_tiles(cnt_.t_done, t_new);
     }
 
     void finish_count() {

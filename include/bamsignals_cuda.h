@@ -67,7 +67,9 @@ typedef struct bsg_opts {
                                  record data is never cached: every call reads, inflates and decodes the file again) */
     int32_t gpu_inflate;      /* 0 (default) or 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the
                                  device (the host only ships compressed bytes); -1: host zlib worker pool */
-    int32_t reserved[8];
+    int32_t stream_min_ints;  /* result ints that must be final before a portion is counted + shipped while later
+                                 batches are still inflating; 0 = default (4 Mi), -1 = never (one pass at the end) */
+    int32_t reserved[7];
 } bsg_opts;
 
 /* Counters and timings of the last call on this thread (milliseconds; kernel times from CUDA events on the

@@ -229,3 +229,37 @@ def test_gpu_inflate_corrupt_stream(tmp_path, fixture_bam):
             B.bamCount(p, gr, opts=B.default_opts(**GPUI))
         assert e.value.code == -4
     assert np.array_equal(B.bamCount(fixture_bam, gr, opts=B.default_opts(**GPUI)), O.bamCount(fixture_bam, gr))
+
+
+# ---- streaming finalisation: tiles are counted + shipped batch by batch ------------------------------------------------
+@pytest.mark.parametrize("preset,gs", [("c2", 0.004), ("c3", 0.004), ("c4", 0.002), ("c5", 0.002)])
+@pytest.mark.parametrize("stream", [1, -1])
+def test_streaming_finalisation_small_batches(gen_dir, preset, gs, stream):
+    """Tiny batches + a 1-int streaming threshold force the mid-pipeline path (filter new rows, join + count the tiles
+    the frontier has passed, ship them) on every batch; -1 is the single pass at the end.  Both must match the oracle."""
+    bam, _ = WL.make_bam(preset, gs, gen_dir, unplaced=7)
+    gr, kw, fn = WL.regions(preset, gs)
+    want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    for batch in (1 << 16, 1 << 19):
+        got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch, stream_min_ints=stream), **kw)
+        t = B.timings()
+        assert np.array_equal(WL.as_flat(got), want)
+        if stream > 0 and batch == (1 << 16):
+            assert t["n_launches"] > 3 * t["n_batches"]          # decode + inflate/walks per batch, plus the count launches
+
+
+def test_streaming_with_shuffled_and_overlapping_regions(gen_dir):
+    """Caller order != genomic order, duplicated and nested regions, '-' strand tiles wider than one tile."""
+    bam, _ = WL.make_bam("c3", 0.004, gen_dir)
+    L = WL.contig_lens("c3", 0.004)[0]
+    rng = np.random.default_rng(12)
+    n = 400
+    start = rng.integers(1, L - 40000, n)
+    width = rng.integers(1, 40000, n)
+    start[::7] = start[0]
+    width[::7] = width[0]
+    gr = B.GRanges(["chr1"] * n, start, width, rng.choice(["+", "-", "*"], n).tolist())
+    o = B.default_opts(batch_bytes=1 << 17, stream_min_ints=1)
+    same(B.bamCoverage(bam, gr, paired_end="extend", opts=o).as_list(), O.bamCoverage(bam, gr, paired_end="extend", nthreads=8).as_list())
+    same(B.bamProfile(bam, gr, binsize=3, ss=True, shift=40, opts=o).as_list(), O.bamProfile(bam, gr, binsize=3, ss=True, shift=40, nthreads=8).as_list())
+    assert np.array_equal(B.bamCount(bam, gr, ss=True, paired_end="midpoint", opts=o), O.bamCount(bam, gr, ss=True, paired_end="midpoint", nthreads=8))

@@ -145,48 +145,122 @@ void BamFile::parse_header() {
     else first_rec_ = block_coff[k] << 16 | uint64_t(p - block_start_u[k]);
 }
 
+namespace {
+
+// Whole index file into memory; a BGZF-compressed one (.csi files are) is inflated block by block.
+std::vector<uint8_t> read_index_file(FILE* fp, const std::string& what) {
+    std::vector<uint8_t> d;
+    uint8_t tmp[1 << 16];
+    size_t k;
+    while ((k = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + k);
+    if (d.size() < 4 || !(d[0] == 0x1f && d[1] == 0x8b)) return d;
+    std::vector<uint8_t> out;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) fail(BSG_ENOMEM, "zlib inflateInit2 failed");
+    size_t p = 0;
+    bool ok = true;
+    while (ok && p + 18 <= d.size()) {
+        const uint8_t* h = d.data() + p;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { ok = false; break; }
+        const uint32_t xlen = rd_u16(h + 10);
+        int bsize = -1;
+        for (uint32_t q = 0; q + 4 <= xlen && p + 12 + q + 4 <= d.size();) {
+            const uint8_t* e = h + 12 + q;
+            const uint32_t slen = rd_u16(e + 2);
+            if (e[0] == 'B' && e[1] == 'C' && slen == 2 && q + 6 <= xlen) bsize = rd_u16(e + 4);
+            q += 4 + slen;
+        }
+        if (bsize < 0 || uint32_t(bsize) + 1 < 12 + xlen + 8 || p + uint32_t(bsize) + 1 > d.size()) { ok = false; break; }
+        const uint32_t csize = uint32_t(bsize) + 1, isize = rd_u32(h + csize - 4);
+        if (isize > 65536) { ok = false; break; }
+        const size_t old = out.size();
+        out.resize(old + isize);
+        if (isize) {
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef*>(h + 12 + xlen);
+            zs.avail_in = csize - 12 - xlen - 8;
+            zs.next_out = out.data() + old;
+            zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (!(rc == Z_STREAM_END && zs.avail_out == 0) ||
+                uint32_t(crc32(crc32(0L, Z_NULL, 0), out.data() + old, isize)) != rd_u32(h + csize - 8)) { ok = false; break; }
+        }
+        p += csize;
+    }
+    inflateEnd(&zs);
+    if (!ok || p != d.size()) fail(BSG_EFORMAT, "corrupt BGZF-compressed index for " + what);
+    return out;
+}
+
+}  // namespace
+
+// Index discovery follows htslib's order for a BAM file: <path>.csi, <path minus .bam>.csi, <path>.bai,
+// <path minus .bam>.bai; the format is decided by the magic, not by the file name.  Both formats end up in the same
+// RefIndex: a CSI index (SAM spec "CSIv1": min_shift / depth in the header, a per-bin `loffset` instead of the linear
+// index) has its linear index rebuilt from the loffsets - loffset(bin) is the linear-index entry of the bin's first
+// window (htslib's update_loff), i.e. the offset of the first record overlapping that window.
 void BamFile::load_index() {
-    std::string cand[2] = {path_ + ".bai", ""};
-    if (path_.size() > 4 && path_.compare(path_.size() - 4, 4, ".bam") == 0) cand[1] = path_.substr(0, path_.size() - 4) + ".bai";
+    std::vector<std::string> cand = {path_ + ".csi"};
+    const bool has_ext = path_.size() > 4 && path_.compare(path_.size() - 4, 4, ".bam") == 0;
+    if (has_ext) cand.push_back(path_.substr(0, path_.size() - 4) + ".csi");
+    cand.push_back(path_ + ".bai");
+    if (has_ext) cand.push_back(path_.substr(0, path_.size() - 4) + ".bai");
     std::vector<uint8_t> d;
     bool found = false;
     for (auto& c : cand) {
-        if (c.empty()) continue;
         FILE* fp = fopen(c.c_str(), "rb");
         if (!fp) continue;
-        uint8_t tmp[1 << 16];
-        size_t k;
-        while ((k = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + k);
         struct stat st;
         if (fstat(fileno(fp), &st) == 0) {
             index_size_ = uint64_t(st.st_size);
             index_mtime_ns_ = uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec);
         }
         index_path_ = c;
+        try { d = read_index_file(fp, path_); } catch (...) { fclose(fp); throw; }
         fclose(fp);
         found = true;
         break;
     }
     if (!found) fail(BSG_ENOINDEX, "BAM indexing file is not available for file " + path_);   // src/bamsignals.cpp:209
     size_t p = 0;
-    auto need = [&](size_t n) { if (p + n > d.size()) fail(BSG_EFORMAT, "truncated BAI index for " + path_); };
+    auto need = [&](size_t n) { if (p + n > d.size()) fail(BSG_EFORMAT, "truncated BAM index for " + path_); };
     need(8);
-    if (memcmp(d.data(), "BAI\1", 4) != 0) fail(BSG_EFORMAT, "bad BAI magic for " + path_);
-    int32_t n_ref = rd_i32(d.data() + 4);
-    p = 8;
-    if (n_ref < 0) fail(BSG_EFORMAT, "corrupt BAI index for " + path_);
+    const bool csi = memcmp(d.data(), "CSI\1", 4) == 0;
+    if (!csi && memcmp(d.data(), "BAI\1", 4) != 0) fail(BSG_EFORMAT, "bad BAM index magic for " + path_);
+    p = 4;
+    if (csi) {
+        need(12);
+        min_shift_ = rd_i32(d.data() + p);
+        depth_ = rd_i32(d.data() + p + 4);
+        const int32_t l_aux = rd_i32(d.data() + p + 8);
+        p += 12;
+        if (min_shift_ < 1 || min_shift_ > 30 || depth_ < 1 || depth_ > 9 || min_shift_ + 3 * depth_ > 40 || l_aux < 0)
+            fail(BSG_EFORMAT, "unsupported CSI index geometry for " + path_);
+        need(size_t(l_aux));
+        p += size_t(l_aux);
+    }
+    need(4);
+    const int32_t n_ref = rd_i32(d.data() + p);
+    p += 4;
+    if (n_ref < 0) fail(BSG_EFORMAT, "corrupt BAM index for " + path_);
+    const uint32_t first_leaf = uint32_t(((1ull << (3 * depth_)) - 1) / 7), n_leaf = 1u << (3 * depth_);
+    meta_bin_ = uint32_t(((1ull << (3 * (depth_ + 1))) - 1) / 7) + 1;                      // 37450 for a BAI
     refs_.resize(n_ref);
     entries_.push_back(first_rec_);
     for (int r = 0; r < n_ref; ++r) {
+        RefIndex& ri = refs_[r];
         need(4);
         int32_t n_bin = rd_i32(d.data() + p);
         p += 4;
         for (int b = 0; b < n_bin; ++b) {
-            need(8);
-            uint32_t bin = rd_u32(d.data() + p);
+            need(csi ? 16 : 8);
+            const uint32_t bin = rd_u32(d.data() + p);
+            uint64_t loff = 0;
+            if (csi) { loff = rd_u64(d.data() + p + 4); p += 8; }
             int32_t n_chunk = rd_i32(d.data() + p + 4);
             p += 8;
-            if (n_chunk < 0) fail(BSG_EFORMAT, "corrupt BAI index for " + path_);
+            if (n_chunk < 0) fail(BSG_EFORMAT, "corrupt BAM index for " + path_);
             need(16ull * n_chunk);
             std::vector<VRange> cs(n_chunk);
             for (int c = 0; c < n_chunk; ++c) {
@@ -194,39 +268,51 @@ void BamFile::load_index() {
                 cs[c].end = rd_u64(d.data() + p + 8);
                 p += 16;
             }
-            if (bin == 37450) {   // pseudo-bin: chunk 0 = (ref_beg, ref_end) offsets, chunk 1 = read counts
+            if (bin == meta_bin_) {   // pseudo-bin: chunk 0 = (ref_beg, ref_end) offsets, chunk 1 = read counts
                 if (n_chunk >= 1 && cs[0].end > cs[0].beg) { entries_.push_back(cs[0].beg); entries_.push_back(cs[0].end); }
-            } else {
-                for (auto& c : cs) { entries_.push_back(c.beg); entries_.push_back(c.end); }
+                ri.bins[bin] = std::move(cs);
+                continue;
             }
-            if (bin != 37450)
-                for (auto& c : cs) {
-                    if (c.end <= c.beg) continue;
-                    if (refs_[r].ref_end <= refs_[r].ref_beg) { refs_[r].ref_beg = c.beg; refs_[r].ref_end = c.end; }
-                    refs_[r].ref_beg = std::min(refs_[r].ref_beg, c.beg);
-                    refs_[r].ref_end = std::max(refs_[r].ref_end, c.end);
-                }
-            if (bin >= 4681 && bin < 37449 + 1) {
+            if (bin >= first_leaf + n_leaf) fail(BSG_EFORMAT, "bin number out of range in the index of " + path_);
+            for (auto& c : cs) { entries_.push_back(c.beg); entries_.push_back(c.end); }
+            for (auto& c : cs) {
+                if (c.end <= c.beg) continue;
+                if (ri.ref_end <= ri.ref_beg) { ri.ref_beg = c.beg; ri.ref_end = c.end; }
+                ri.ref_beg = std::min(ri.ref_beg, c.beg);
+                ri.ref_end = std::max(ri.ref_end, c.end);
+            }
+            if (csi && loff) {
+                // first window of the bin (htslib's hts_bin_bot): level l has 8^l bins of 8^(depth-l) windows each
+                int l = 0;
+                uint32_t first = 0;
+                while (l < depth_ && bin >= first + (1u << (3 * l))) { first += 1u << (3 * l); ++l; }
+                const uint64_t w = uint64_t(bin - first) << (3 * (depth_ - l));
+                if (ri.linear.size() <= w) ri.linear.resize(w + 1, 0);
+                ri.linear[w] = ri.linear[w] ? std::min(ri.linear[w], loff) : loff;
+                entries_.push_back(loff);
+            }
+            if (bin >= first_leaf) {
                 // Leaf bins go into a flat per-window array: the file is coordinate-sorted, so the chunks of a run of
                 // consecutive leaf bins lie between the first bin's first chunk and the last bin's last chunk.
-                const size_t w = bin - 4681;
-                if (refs_[r].leaf.size() <= w) refs_[r].leaf.resize(w + 1, VRange{0, 0});
+                const size_t w = bin - first_leaf;
+                if (ri.leaf.size() <= w) ri.leaf.resize(w + 1, VRange{0, 0});
                 VRange lr{~0ull, 0};
                 for (auto& c : cs) { lr.beg = std::min(lr.beg, c.beg); lr.end = std::max(lr.end, c.end); }
-                if (lr.end > lr.beg) refs_[r].leaf[w] = lr;
+                if (lr.end > lr.beg) ri.leaf[w] = lr;
             } else {
-                refs_[r].bins[bin] = std::move(cs);
+                ri.bins[bin] = std::move(cs);
             }
         }
+        if (csi) continue;
         need(4);
         int32_t n_intv = rd_i32(d.data() + p);
         p += 4;
-        if (n_intv < 0) fail(BSG_EFORMAT, "corrupt BAI index for " + path_);
+        if (n_intv < 0) fail(BSG_EFORMAT, "corrupt BAM index for " + path_);
         need(8ull * n_intv);
-        refs_[r].linear.resize(n_intv);
+        ri.linear.resize(n_intv);
         for (int i = 0; i < n_intv; ++i) {
-            refs_[r].linear[i] = rd_u64(d.data() + p + 8ull * i);
-            if (refs_[r].linear[i]) entries_.push_back(refs_[r].linear[i]);
+            ri.linear[i] = rd_u64(d.data() + p + 8ull * i);
+            if (ri.linear[i]) entries_.push_back(ri.linear[i]);
         }
         p += 8ull * n_intv;
     }
@@ -238,7 +324,7 @@ void BamFile::load_index() {
 
 int64_t BamFile::bp_per_block(int tid) const {
     if (tid < 0 || tid >= int(refs_.size()) || tid >= int(lens_.size())) return 16384;
-    auto meta = refs_[tid].bins.find(37450);
+    auto meta = refs_[tid].bins.find(meta_bin_);
     uint64_t beg = 0, end = 0;
     if (meta != refs_[tid].bins.end() && !meta->second.empty()) { beg = meta->second[0].beg >> 16; end = meta->second[0].end >> 16; }
     else {
@@ -256,7 +342,7 @@ uint64_t BamFile::approx_coffset(int tid, int64_t pos) const {
     // offsets grow with (tid, pos) in a coordinate-sorted file; references without reads inherit the next one's start
     for (int t = std::max(tid, 0); t < int(refs_.size()); ++t) {
         const auto& lin = refs_[t].linear;
-        size_t w = t == tid ? size_t(std::max<int64_t>(0, pos) >> 14) : 0;
+        size_t w = t == tid ? size_t(std::max<int64_t>(0, pos) >> min_shift_) : 0;
         for (; w < lin.size(); ++w) if (lin[w]) return lin[w] >> 16;
     }
     return size_;
@@ -274,11 +360,11 @@ void BamFile::query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out)
     const RefIndex& ri = refs_[tid];
     if (beg < 0) beg = 0;
     if (end <= beg || ri.ref_end <= ri.ref_beg) return;
-    // Lower bound L: the linear index gives the first record overlapping the 16 kb window of `beg`; every record
+    // Lower bound L: the linear index gives the first record overlapping the window (16 kb for a BAI) of `beg`; every record
     // overlapping [beg, ...) lies at or behind it (htslib uses the same bound as `min_off`).
     uint64_t lo = ri.ref_beg;
     if (!ri.linear.empty()) {
-        const size_t w = size_t(beg >> 14);
+        const size_t w = size_t(beg >> min_shift_);
         uint64_t v = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
         // some indexers leave zero entries for windows no read overlaps; walk back to the last filled one
         if (v == 0 && w < ri.linear.size())
@@ -289,7 +375,7 @@ void BamFile::query(int tid, int64_t beg, int64_t end, std::vector<VRange>* out)
     // first non-empty leaf bin > window(end-1)) starts at pos >= end, and the file is coordinate-sorted, so nothing at
     // or behind it can overlap [beg, end).  This plays the role of the iterator's "pos >= end -> stop" rule.
     uint64_t hi = ri.ref_end;
-    for (size_t w = size_t((end - 1) >> 14) + 1; w < ri.leaf.size(); ++w)
+    for (size_t w = size_t((end - 1) >> min_shift_) + 1; w < ri.leaf.size(); ++w)
         if (ri.leaf[w].end) { hi = std::min(hi, ri.leaf[w].beg); break; }
     if (hi > lo) out->push_back(VRange{lo, hi});
 }

@@ -1,4 +1,4 @@
-// Host-side BAM / BGZF / BAI access for the fetch pipeline (no htslib offline: SURVEY.md App. B).
+// Host-side BAM / BGZF / BAI + CSI access for the fetch pipeline (no htslib offline: SURVEY.md App. B).
 // Replaces what the reference gets from htslib through `Bamfile` (src/bamsignals.cpp:195-220): open + index load,
 // header lookup (bam_name2id, :27) and the region -> virtual-offset query behind bam_itr_queryi (:267).
 #pragma once
@@ -60,7 +60,7 @@ public:
 
     // Identity of the file contents for the resident-table cache.
     uint64_t mtime_ns() const { return mtime_ns_; }
-    bool index_unchanged() const;   // the .bai on disk still has the size and mtime it had when it was parsed
+    bool index_unchanged() const;   // the index on disk still has the size and mtime it had when it was parsed
 
 private:
     struct RefIndex {
@@ -85,6 +85,8 @@ private:
     uint64_t first_rec_ = 0;
     std::vector<RefIndex> refs_;
     std::vector<uint64_t> entries_;
+    int min_shift_ = 14, depth_ = 5;     // index geometry: BAI is fixed at 14 / 5, a CSI header states its own
+    uint32_t meta_bin_ = 37450;
 };
 
 // Raw-DEFLATE inflate of one BGZF block into dst[0..isize); zlib state is per worker thread.

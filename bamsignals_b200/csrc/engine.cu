@@ -76,7 +76,7 @@ struct DeviceCtx {
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
-    DevBuf tab[5], c0, c1, tiles_i32, tiles_i64, out, scalars;
+    DevBuf tab[2], c0, c1, tiles_i32, tiles_i64, out, scalars;
     DevBuf raw_all, offs_all, batch_table;      // resident raw bytes of a staged session
     DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
     PinBuf h_total;
@@ -273,6 +273,8 @@ public:
         for (size_t i = 0; i < segs_.size();) {
             auto b = std::make_unique<Batch>();
             b->seg_first = i;
+            // (Measured: batches well below 1 GiB leave the inflate kernel, one warp per BGZF block, with fewer blocks
+            // than the 148 x 28 warps the GPU holds - a 128 MiB ... 1 GiB ramp cost C2 30 ms end to end.)
             uint64_t acc = 0;
             while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= uint64_t(batch_bytes))) {
                 acc += (segs_[i].usize + 15) & ~15ull;
@@ -330,15 +332,15 @@ public:
         tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
     }
 
-    // Staged sessions: decode every resident raw batch again (K1) in ONE launch, timed.
-    void decode_resident() {
+    // Staged sessions: decode + filter every resident raw batch again (K1) in ONE launch, timed.
+    void decode_resident(Mode mode, const FilterParams& fp) {
         DeviceCtx& c = *ctx_;
         BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
         if (resident_.empty()) return;
         Span sp{c.timing_event(), c.timing_event()};
         BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
         launch_decode_table(c.batch_table.as<DecodeBatch>(), int(resident_.size()), resident_chunks_, table(),
-                            c.scalars.as<DeviceScalars>(), c.s_comp);
+                            mode == MODE_COVERAGE, fp, c.scalars.as<DeviceScalars>(), c.s_comp);
         BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
         kt_.decode.push_back(sp); kt_.launches += 1;
     }
@@ -448,11 +450,11 @@ public:
         if (cnt_.want_output) start_streamer();
     }
 
-    // Rows [0, rows) of the read table are decoded and `frontier` = (tid, pos) of the last of them: filter the new rows
-    // and count + ship every tile that can no longer change.
+    // Rows [0, rows) of the read table are decoded + filtered and `frontier` = (tid, pos) of the last of them:
+    // count + ship every tile that can no longer change.
     void advance(int64_t rows, uint32_t f_tid, int32_t f_pos) {
         if (!cnt_.active) return;
-        filter_rows(rows);
+        cnt_.rows_ready = rows;
         const uint64_t key = uint64_t(f_tid) << 32 | uint64_t(uint32_t(std::max(f_pos, 0)));
         const int64_t t_new = std::upper_bound(tile_final_key_.begin(), tile_final_key_.end(), key) - tile_final_key_.begin();
         // worth a launch + copy only in decent portions
@@ -463,7 +465,7 @@ public:
 
     void finish_count() {
         DeviceCtx& c = *ctx_;
-        filter_rows(n_rows_);
+        cnt_.rows_ready = n_rows_;
         if (n_tiles_ > cnt_.t_done) count_tiles(cnt_.t_done, n_tiles_);
         DeviceScalars* sc = c.scalars.as<DeviceScalars>();
         BSG_CUDA(cudaGetLastError());
@@ -478,7 +480,8 @@ public:
         const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
         check_status(hs->status);
         tm_.records = n_rows_;
-        tm_.records_kept = int64_t(hs->kept);
+        tm_.records_kept = 0;
+        for (int k = 0; k < kKeptSlots; ++k) tm_.records_kept += int64_t(hs->kept[k * kKeptStride]);
         tm_.candidates = int64_t(hs->candidates);
     }
 
@@ -498,26 +501,13 @@ private:
         int32_t* out = nullptr;
         const int64_t* out_offsets = nullptr;
         int32_t* const* out_ptrs = nullptr;
-        int64_t rows_filtered = 0, t_done = 0;
+        int64_t rows_ready = 0, t_done = 0;
     };
     struct OutJob { int slot; int64_t t0, t1; cudaEvent_t computed; };
 
     cudaStream_t cnt_stream() const { return hi_prio_ ? ctx_->s_hi : ctx_->s_comp; }
 
-    void filter_rows(int64_t rows) {
-        DeviceCtx& c = *ctx_;
-        if (rows <= cnt_.rows_filtered) return;
-        cudaStream_t st = cnt_stream();
-        Span sp{c.timing_event(), c.timing_event()};
-        BSG_CUDA(cudaEventRecord(sp.a, st));
-        if (cnt_.mode == MODE_COVERAGE) launch_filter_coverage(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), st);
-        else launch_filter_pileup(table(), cnt_.rows_filtered, rows, cnt_.fp, c.c0.as<int32_t>(), c.c1.as<int32_t>(), c.scalars.as<DeviceScalars>(), st);
-        BSG_CUDA(cudaEventRecord(sp.b, st));
-        kt_.filter.push_back(sp); kt_.launches += 1;
-        cnt_.rows_filtered = rows;
-    }
-
-    // K3 + K4/K5 for tiles [t0, t1) over the rows filtered so far, then hand them to the output streamer
+    // K3 + K4/K5 for tiles [t0, t1) over the rows decoded so far, then hand them to the output streamer
     void count_tiles(int64_t t0, int64_t t1) {
         DeviceCtx& c = *ctx_;
         cudaStream_t st = cnt_stream();
@@ -531,7 +521,7 @@ private:
         {
             Span sp{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sp.a, st));
-            launch_join(table(), cnt_.rows_filtered, tt, n, sc, st);
+            launch_join(table(), cnt_.rows_ready, tt, n, sc, st);
             BSG_CUDA(cudaEventRecord(sp.b, st));
             kt_.join.push_back(sp); kt_.launches += 1;
         }
@@ -662,17 +652,15 @@ public:
     void reset_counters() { int nd = tm_.n_devices; int64_t bc = tm_.bytes_compressed, bi = tm_.bytes_inflated, nb = tm_.n_batches;
         memset(&tm_, 0, sizeof tm_); tm_.n_devices = nd; tm_.bytes_compressed = bc; tm_.bytes_inflated = bi; tm_.n_batches = nb; }
 
-    int64_t n_rows() const { return n_rows_; }
-
 private:
     ReadTable table() {
         DeviceCtx& c = *ctx_;
-        return ReadTable{c.tab[0].as<int32_t>(), c.tab[1].as<int32_t>(), c.tab[2].as<int32_t>(), c.tab[3].as<int32_t>(), c.tab[4].as<uint32_t>()};
+        return ReadTable{c.tab[0].as<int32_t>(), c.tab[1].as<int32_t>(), c.c0.as<int32_t>(), c.c1.as<int32_t>()};
     }
     void ensure_table(int64_t rows) {
         DeviceCtx& c = *ctx_;
         const size_t bytes = size_t(rows + 4) * 4;
-        for (auto& b : c.tab) b.ensure(bytes);
+        for (auto& b : c.tab) b.ensure(bytes);   // tid, pos
         c.c0.ensure(bytes); c.c1.ensure(bytes);
     }
 
@@ -806,7 +794,9 @@ private:
                 BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
                 Span sp{c.timing_event(), c.timing_event()};
                 BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-                launch_decode(DecodeBatch{d_raw, d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_comp);
+                if (!cnt_.active) fail(BSG_EARG, "internal error: streaming decode without a counting call");
+                launch_decode(DecodeBatch{d_raw, d_offs, n_rows_, int32_t(n), 0}, table(), cnt_.mode == MODE_COVERAGE, cnt_.fp,
+                              c.scalars.as<DeviceScalars>(), c.s_comp);
                 BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
                 BSG_CUDA(cudaEventRecord(c.ev_free[slot], c.s_comp));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
@@ -860,7 +850,9 @@ private:
                 BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_total[p.slot], 0));
                 Span sp{c.timing_event(), c.timing_event()};
                 BSG_CUDA(cudaEventRecord(sp.a, c.s_hi));
-                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), c.scalars.as<DeviceScalars>(), c.s_hi);
+                if (!cnt_.active) fail(BSG_EARG, "internal error: streaming decode without a counting call");
+                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), cnt_.mode == MODE_COVERAGE, cnt_.fp,
+                              c.scalars.as<DeviceScalars>(), c.s_hi);
                 BSG_CUDA(cudaEventRecord(sp.b, c.s_hi));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
                 if (n > 0 && cnt_.active) {
@@ -1341,8 +1333,8 @@ int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual
         st->s->reset_counters();
         (void)ext_pileup(tlen_filter, shift, pe_mid);
         st->s->prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
-        st->s->decode_resident();
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
+        st->s->decode_resident(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp);
         st->s->count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, out, out_offsets, nullptr, out != nullptr);
         st->s->finish_timings(t0);
     });
@@ -1356,8 +1348,8 @@ int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqu
         st->s->reset_counters();
         (void)ext_coverage(tlen_filter, tspan);
         st->s->prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
-        st->s->decode_resident();
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
+        st->s->decode_resident(MODE_COVERAGE, fp);
         st->s->count(MODE_COVERAGE, fp, 1, 0, out, out_offsets, nullptr, out != nullptr);
         st->s->finish_timings(t0);
     });

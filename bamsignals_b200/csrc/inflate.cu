@@ -41,6 +41,36 @@ struct Q2Smem {
     uint32_t q[inflate_core::kQueue];
 };
 
+// fill_queue's table lookups and queue stores through explicit shared-space addresses (kept in registers)
+struct SmemAccess {
+    uint32_t lit_a, dist_a, q_a;
+    __device__ __forceinline__ uint32_t lit(uint32_t byte_off) const {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(lit_a + byte_off) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ uint32_t dist(uint32_t byte_off) const {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(dist_a + byte_off) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ void put(uint32_t byte_off, uint32_t v) const {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_a + byte_off), "r"(v) : "memory");
+    }
+    template <bool DIST> __device__ __forceinline__ uint32_t count(uint32_t len) const {
+        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_count) : offsetof(inflate_core::Tables, lit_count);
+        uint32_t r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + 2u * len) : "memory");
+        return r;
+    }
+    template <bool DIST> __device__ __forceinline__ uint32_t sorted(uint32_t i) const {
+        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_sorted) : offsetof(inflate_core::Tables, lit_sorted);
+        uint32_t r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + 2u * i) : "memory");
+        return r;
+    }
+};
+
 __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
                                                                   const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
@@ -50,15 +80,23 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
     if (b >= n_blocks) return;
     Tables& T = s_mem[wid].T;
     volatile uint32_t* q = s_mem[wid].q;
+    SmemAccess acc{uint32_t(__cvta_generic_to_shared(s_mem[wid].T.lit)), uint32_t(__cvta_generic_to_shared(s_mem[wid].T.dist)),
+                   uint32_t(__cvta_generic_to_shared(s_mem[wid].q))};
+    // identity shuffle: ptxas cannot re-derive the value from %tid inside the decode loop (it otherwise rebuilds the
+    // address with six instructions per token); dist and q are fixed offsets from it
+    acc.lit_a = __shfl_sync(FULL, acc.lit_a, lane);
+    acc.dist_a = acc.lit_a + uint32_t(sizeof(uint32_t) << kLitBits);
+    acc.q_a = acc.lit_a + uint32_t(sizeof(inflate_core::Tables));
     const InflateBlock blk = blocks[b];
     uint8_t* out = raw + blk.out_off;
     const uint32_t out_len = blk.out_len;
     inflate_core::BitReader br;
-    br.wp = nullptr; br.p0 = nullptr; br.w0 = br.w1 = br.w2 = br.bo = br.first_bit = 0;
-    if (lane == 0) br.init(comp + blk.in_off);
+    br.base = reinterpret_cast<const uint32_t*>(comp);     // cudaMalloc'ed: aligned
+    br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
+    if (lane == 0) br.init(br.base, blk.in_off);
+    const uint64_t end_bit = (uint64_t(blk.in_off) + blk.in_len) * 8u;
     uint32_t op_dec = 0, pos_base = 0;
     int phase = 0, last = 0;
-    uint64_t stored_bits = 0;       // bits consumed before the last reader re-init (stored blocks)
     for (;;) {
         int nq = 0, state = 0;       // state: 0 = go on, 1 = stream finished, 2 = error
         if (lane == 0) {
@@ -70,13 +108,13 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
                     const uint32_t v = br.peek();
                     br.consume(32);
                     const uint32_t len = v & 0xffffu, nlen = v >> 16;
-                    if ((len ^ nlen) != 0xffffu || op_dec + len > out_len) state = 2;
+                    const uint32_t src_off = br.byte_pos();
+                    if ((len ^ nlen) != 0xffffu || op_dec + len > out_len || (uint64_t(src_off) + len) * 8u > end_bit) state = 2;
                     else {
-                        const uint8_t* src = br.byte_ptr();
+                        const uint8_t* src = comp + src_off;
                         for (uint32_t j = 0; j < len; ++j) out[op_dec + j] = src[j];
                         op_dec += len;
-                        stored_bits += br.bits_used() + uint64_t(len) * 8;
-                        br.init(src + len);
+                        br.init(br.base, src_off + len);
                         q[0] = kTokSkip | len;
                         nq = 1;
                         if (last) state = 1;
@@ -85,9 +123,9 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
             }
             if (phase == 1 && nq == 0 && state == 0) {
                 int eob = 0, bad = 0;
-                nq = fill_queue(br, T, q, &op_dec, &eob, &bad);
+                nq = fill_queue(br, acc, &op_dec, &eob, &bad);
                 if (eob) { phase = 0; if (last) state = 1; }
-                if (bad || op_dec > out_len || stored_bits + br.bits_used() > uint64_t(blk.in_len) * 8) state = 2;
+                if (bad || op_dec > out_len || br.bit_pos() > end_bit) state = 2;
             }
         }
         nq = __shfl_sync(FULL, nq, 0);

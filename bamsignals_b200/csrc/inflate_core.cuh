@@ -22,8 +22,9 @@ constexpr int kQueue = 256;
 // token: literal = byte ; match = 1 << 31 | (dist - 1) << 16 | len ; skip (stored bytes already in place) = 1 << 30 | len
 constexpr uint32_t kTokMatch = 0x80000000u, kTokSkip = 0x40000000u;
 
-// decode-table entry: [3:0] code length (0 = not in the primary table), [7:4] extra-bit count, [9:8] type,
-// [31:16] literal byte / length base / distance base
+// decode-table entry: [3:0] code length, [7:4] extra-bit count, [9:8] type, [31:16] literal byte / length base /
+// distance base.  Slots no code of <= kLitBits (kDistBits) bits maps to hold kTypeBad with length 0: one type test
+// sends literals and lengths down their fast paths and everything rare (end of block, long codes, errors) elsewhere.
 enum : uint32_t { kTypeLit = 0u << 8, kTypeLen = 1u << 8, kTypeEob = 2u << 8, kTypeBad = 3u << 8, kTypeMask = 3u << 8 };
 
 BSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -45,28 +46,34 @@ BSG_HD uint32_t rev_bits(uint32_t code, uint32_t len) {
 }
 
 // Bit reader over aligned 32-bit words with two words of look-ahead: peek() is one funnel shift, consume() is an
-// add plus a predicated word rotation whose load was issued a word earlier.
+// add plus a predicated word rotation whose load was issued a word earlier.  Positions are 32-bit word indices into
+// one 4-byte aligned buffer (the batch's compressed bytes), so the state is five 32-bit registers.
 struct BitReader {
-    const uint32_t* wp;    // next word to load
-    const uint32_t* p0;    // first word
-    uint32_t w0, w1, w2, bo, first_bit;
-    BSG_HD void init(const uint8_t* in) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(in);
-        p0 = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-        first_bit = uint32_t(a & 3) * 8;
-        w0 = p0[0]; w1 = p0[1]; w2 = p0[2];
-        wp = p0 + 3;
-        bo = first_bit;
+    const uint32_t* base;  // the buffer (uniform for all blocks of a launch)
+    uint32_t wi;           // index of the next word to load
+    uint32_t w0, w1, w2, bo;
+    BSG_HD void init(const uint32_t* buf, uint32_t byte_off) {
+        base = buf;
+        wi = byte_off >> 2;
+        bo = (byte_off & 3u) * 8u;
+        w0 = base[wi]; w1 = base[wi + 1]; w2 = base[wi + 2];
+        wi += 3;
     }
     BSG_HD uint32_t peek() const { return funnel_r(w0, w1, bo); }           // next 32 bits
-    BSG_HD void consume(uint32_t n) {                                         // n <= 32
+    BSG_HD uint32_t peek_hi() const { return funnel_r(w1, w2, bo); }        // the 32 bits after those
+    BSG_HD void consume_short(uint32_t n) {                                   // n <= 32
         bo += n;
-        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = *wp++; }
+        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
     }
-    BSG_HD uint64_t bits_used() const { return uint64_t(wp - p0 - 3) * 32 + bo - first_bit; }
-    BSG_HD const uint8_t* byte_ptr() const {                                  // only valid when bo is a multiple of 8
-        return reinterpret_cast<const uint8_t*>(wp - 3) + (bo >> 3);
+    BSG_HD void consume(uint32_t n) {                                         // n <= 64
+        bo += n;
+        if (bo >= 32) {
+            bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++];
+            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
+        }
     }
+    BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 32u + bo; }  // bits from the start of the buffer
+    BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 4u + (bo >> 3); }   // only valid when bo is a multiple of 8
 };
 
 struct Tables {
@@ -97,14 +104,15 @@ BSG_HD uint32_t dist_entry(int sym, int len) {
 }
 
 // canonical decode of a code longer than the primary table (RFC 1951 3.2.2) from the 32 peeked bits;
-// returns the symbol and its code length, or -1
-BSG_HD int slow_symbol(uint32_t v, const uint16_t* count, const uint16_t* sorted, int* len_out) {
+// returns the symbol and its code length, or -1.  DIST selects the distance code's count / sorted arrays.
+template <bool DIST, class A>
+BSG_HD int slow_symbol(uint32_t v, const A& acc, int* len_out) {
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
         code |= int(v & 1u);
         v >>= 1;
-        const int c = count[len];
-        if (code - c < first) { *len_out = len; return sorted[index + (code - first)]; }
+        const int c = int(acc.template count<DIST>(uint32_t(len)));
+        if (code - c < first) { *len_out = len; return int(acc.template sorted<DIST>(uint32_t(index + (code - first)))); }
         index += c;
         first += c;
         first <<= 1;
@@ -117,7 +125,7 @@ BSG_HD int slow_symbol(uint32_t v, const uint16_t* count, const uint16_t* sorted
 // Serial table construction by the owning thread.  is_dist selects the entry format.  Returns false when the code
 // is over-subscribed.
 BSG_HD bool build_table(const uint8_t* lens, int n, uint32_t* primary, int bits, uint16_t* count, uint16_t* sorted, bool is_dist) {
-    for (int i = 0; i < (1 << bits); ++i) primary[i] = 0;
+    for (int i = 0; i < (1 << bits); ++i) primary[i] = kTypeBad;   // length 0 + kTypeBad = "not in the primary table"
     int cnt[16];
     for (int l = 0; l < 16; ++l) cnt[l] = 0;
     for (int s = 0; s < n; ++s) cnt[lens[s] & 15]++;
@@ -204,47 +212,78 @@ BSG_HD int read_block_header(BitReader& br, Tables& T, int* last) {
     return ok ? 0 : 2;
 }
 
-// Phase 1: decode symbols into q[0..kQueue) until the queue is full or the block ends.
+// Table / queue access of fill_queue.  The host harness (and any generic caller) uses plain arrays; the kernel
+// passes shared-memory byte addresses and ld.shared / st.shared so that the addresses stay in registers.
+struct ArrayAccess {
+    const Tables* T;
+    uint32_t* q;
+    BSG_HD uint32_t lit(uint32_t byte_off) const { return T->lit[byte_off >> 2]; }
+    BSG_HD uint32_t dist(uint32_t byte_off) const { return T->dist[byte_off >> 2]; }
+    BSG_HD void put(uint32_t byte_off, uint32_t v) const { q[byte_off >> 2] = v; }
+    template <bool DIST> BSG_HD uint32_t count(uint32_t len) const { return DIST ? T->dist_count[len] : T->lit_count[len]; }
+    template <bool DIST> BSG_HD uint32_t sorted(uint32_t i) const { return DIST ? T->dist_sorted[i] : T->lit_sorted[i]; }
+};
+
+// Phase 1: decode symbols into the queue until it holds kQueue tokens or the block ends.
 // *op_dec = bytes decoded so far (updated).  Returns the number of tokens; *eob is set at end-of-block; *bad is
 // sticky (errors do not stop the loop: every access stays in bounds, the caller discards the round).
-template <class Q>
-BSG_HD int fill_queue(BitReader& br, const Tables& T, Q q, uint32_t* op_dec, int* eob, int* bad) {
-    int nq = 0;
+// A match is decoded from ONE 64-bit look-ahead (length code + extra bits <= 20 bits, distance code + extra bits
+// <= 28 bits) and consumed once.
+template <class A>
+BSG_HD int fill_queue(BitReader& br, const A& acc, uint32_t* op_dec, int* eob, int* bad) {
+    constexpr uint32_t kLitMask4 = ((1u << kLitBits) - 1u) << 2, kDistMask4 = ((1u << kDistBits) - 1u) << 2;
+    uint32_t qo = 0;                  // byte offset of the next queue slot
     uint32_t op = *op_dec;
     int err = 0;
     *eob = 0;
-    while (nq < kQueue) {
-        uint32_t v = br.peek();
-        uint32_t e = T.lit[v & ((1u << kLitBits) - 1u)];
-        if (!(e & 15u)) {
-            int l;
-            const int sym = slow_symbol(v, T.lit_count, T.lit_sorted, &l);
-            e = sym < 0 ? (uint32_t(l) | kTypeBad) : lit_entry(sym, l);
+    do {
+        const uint32_t v = br.peek();
+        uint32_t e = acc.lit((v << 2) & kLitMask4);
+        uint32_t type = e & kTypeMask;
+        if (type == kTypeLit) {                       // literal with a short code: the common non-match case
+            acc.put(qo, e >> 16);
+            br.consume_short(e & 15u);
+            qo += 4; ++op;
+            continue;
         }
-        const uint32_t len = e & 15u;
-        const uint32_t type = e & kTypeMask;
-        if (type == kTypeLit) { q[nq++] = e >> 16; ++op; br.consume(len); continue; }
-        if (type != kTypeLen) { br.consume(len); if (type == kTypeEob) *eob = 1; else err = 1; break; }
-        const uint32_t eb = (e >> 4) & 15u;
-        const uint32_t mlen = (e >> 16) + ((v >> len) & ((1u << eb) - 1u));
-        br.consume(len + eb);
-        v = br.peek();
-        uint32_t d = T.dist[v & ((1u << kDistBits) - 1u)];
+        if (type != kTypeLen) {                       // rare: end of block, a code longer than the primary table, garbage
+            if (!(e & 15u)) {
+                int l;
+                const int sym = slow_symbol<false>(v, acc, &l);
+                e = sym < 0 ? (uint32_t(l) | kTypeBad) : lit_entry(sym, l);
+                type = e & kTypeMask;
+            }
+            if (type == kTypeLit) {
+                acc.put(qo, e >> 16);
+                br.consume_short(e & 15u);
+                qo += 4; ++op;
+                continue;
+            }
+            if (type != kTypeLen) {
+                br.consume_short(e & 15u);
+                if (type == kTypeEob) *eob = 1; else err = 1;
+                break;
+            }
+        }
+        const uint32_t len = e & 15u, eb = (e >> 4) & 15u, used = len + eb;
+        const uint32_t mlen = (e >> 16) + ((v >> len) & ~(~0u << eb));
+        const uint32_t v2 = funnel_r(v, br.peek_hi(), used);      // used <= 20
+        uint32_t d = acc.dist((v2 << 2) & kDistMask4);
         if (!(d & 15u)) {
             int l;
-            const int sym = slow_symbol(v, T.dist_count, T.dist_sorted, &l);
+            const int sym = slow_symbol<true>(v2, acc, &l);
             d = sym < 0 ? (uint32_t(l) | kTypeBad) : dist_entry(sym, l);
         }
         const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
-        uint32_t mdist = (d >> 16) + ((v >> dl) & ((1u << deb) - 1u));
-        br.consume(dl + deb);
-        if ((d & kTypeMask) == kTypeBad || mdist > op || mdist == 0) { err = 1; mdist = 1; }
-        q[nq++] = kTokMatch | ((mdist - 1u) << 16) | mlen;
-        op += mlen;
-    }
+        uint32_t mdist = (d >> 16) + ((v2 >> dl) & ~(~0u << deb));
+        br.consume(used + dl + deb);                               // <= 48
+        if ((d & kTypeMask) != 0u || mdist > op) { err = 1; mdist = 1; }
+        acc.put(qo, kTokMatch | ((mdist - 1u) << 16) | mlen);
+        qo += 4; op += mlen;
+    } while (qo < uint32_t(kQueue) * 4u);
     *op_dec = op;
     *bad |= err;
-    return nq;
+    return int(qo >> 2);
 }
 
 }  // namespace inflate_core

@@ -11,11 +11,6 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -23,7 +18,7 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1 decode.  One CTA per chunk of 256 consecutive records, one thread per record.
+// K1 decode + filter.  One CTA per chunk of 256 consecutive records, one thread per record.
 //
 // Records start at arbitrary byte offsets, so a per-thread gather from global memory makes every load instruction
 // touch a dozen 128-byte lines (measured: 15 % of HBM peak).  Instead the CTA's records are one CONTIGUOUS byte span
@@ -93,11 +88,29 @@ __device__ __forceinline__ Decoded decode_one(const LD& ld, uint32_t o, uint32_t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// setRead's filter (src/bamsignals.cpp:328-333, :394-399)
+__device__ __forceinline__ bool keep_read(const FilterParams& p, uint32_t fm, int32_t tlen, int32_t* abs_tlen) {
+    const uint32_t flag = fm & 0xffffu, mapq = fm >> 16;
+    const int32_t a = tlen < 0 ? -tlen : tlen;   // abs() as the reference computes it (INT_MIN stays negative)
+    *abs_tlen = a;
+    bool keep = int32_t(mapq) >= p.mapqual;
+    keep = keep && !(p.required & ~flag);          // every required bit present   (src/bamsignals.cpp:21-23, :328)
+    keep = keep && (p.filtered & ~flag);           // not all filtered bits present (:329); filtered == 0 drops all
+    keep = keep && (!p.have_tlen || (a >= p.tmin && a <= p.tmax));
+    return keep;
+}
+
+// K1+K2 fused: the filter and the pileup / coverage coordinate (setRead, :326-346 and :392-415) are applied to the
+// decoded fields while they are still in registers, so a read costs its raw bytes in and 16 bytes out
+// (tid, pos for the join; c0, c1 for the counting kernels) instead of a 20-byte table row written, read again and
+// turned into 8 more bytes by a second kernel.
+template <bool COVERAGE>
 __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const DecodeBatch* __restrict__ table,
-                                                     int n_batches, ReadTable t, DeviceScalars* sc) {
+                                                     int n_batches, ReadTable t, FilterParams p, DeviceScalars* sc) {
     extern __shared__ __align__(128) uint8_t sm_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_lo, s_bytes;
+    __shared__ int s_kept, s_arrived, s_ghlo, s_ghhi;
     // which batch does this chunk belong to?
     DecodeBatch B = single;
     if (table) {
@@ -127,9 +140,16 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
         } else {
             s_lo = 0; s_bytes = 0;
         }
+        s_kept = 0; s_arrived = 0;
+        // the running halo maxima, read ONCE per CTA (L2, in flight during the copy) and handed to the warps through
+        // shared memory: a warp whose own maxima do not beat them has nothing to publish, and a stale value only costs
+        // a redundant atomicMax.  (Every warp reading them itself put 3.6 M loads on one L2 line: +0.35 ms.)
+        const int2 g = __ldcg(reinterpret_cast<const int2*>(&sc->halo_lo));
+        s_ghlo = g.x; s_ghhi = g.y;
     }
     uint32_t o = 0, rec_end = 0;
     if (active) { o = __ldg(B.offs + i); rec_end = __ldg(B.offs + i + 1); }   // in flight while the bulk copy lands
+    const int lane = threadIdx.x & 31;
     __syncthreads();
     const bool staged = s_bytes != 0;
     if (staged) {
@@ -140,20 +160,40 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
                          : "=r"(done) : "r"(bar_a) : "memory");
     }
     Decoded d;
-    d.tid = -1; d.pos = -1; d.bad = 0;
+    d.tid = -1; d.pos = -1; d.end = -1; d.tlen = 0; d.flagmq = 0; d.bad = 0;
     const SharedLd sld{sm_raw, s_lo};
     const GlobalLd gld{B.raw};
+    int hlo = INT_MIN, hhi = INT_MIN;
+    bool keep = false;
     if (active) {
         d = staged ? decode_one(sld, o, rec_end) : decode_one(gld, o, rec_end);
+        int32_t a;
+        keep = keep_read(p, d.flagmq, d.tlen, &a);
+        const bool neg = (d.flagmq & 0x10u) != 0;
+        int32_t o0, o1;
+        if (!COVERAGE) {
+            const int32_t offset = p.midpoint ? a / 2 + p.shift : p.shift;               // :339
+            const int32_t pos5 = neg ? d.end - offset : d.pos + offset;                  // :340-344
+            o0 = pos5;
+            o1 = keep ? int32_t(neg) : -1;
+            if (keep) { hlo = pos5 - d.pos; hhi = d.pos - pos5; }
+        } else {
+            int32_t s = d.pos, e = d.end;                                                 // :401-403
+            if (p.tspan) {
+                if (neg && d.tlen < 0) s = e + d.tlen + 1;                                // :408-409
+                else if (!neg && d.tlen > 0) e = s + d.tlen - 1;                          // :410-411
+            }
+            o0 = keep ? s : INT_MAX;
+            o1 = keep ? e : INT_MIN;
+            if (keep) { hlo = e - d.pos; hhi = d.pos - s; }
+        }
         const int64_t row = B.row0 + i;
         t.tid[row] = d.tid;
         t.pos[row] = d.pos;
-        t.end[row] = d.end;
-        t.tlen[row] = d.tlen;
-        t.flagmq[row] = d.flagmq;
+        t.c0[row] = o0;
+        t.c1[row] = o1;
     }
     // coordinate-sortedness: compare with the previous record (previous lane; lane 0 re-reads it)
-    const int lane = threadIdx.x & 31;
     uint32_t ptid = __shfl_up_sync(FULL, uint32_t(d.tid), 1);
     int32_t ppos = __shfl_up_sync(FULL, d.pos, 1);
     bool have_prev = active;
@@ -175,77 +215,23 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
     uint32_t bad = d.bad;
     if (have_prev && (uint32_t(d.tid) < ptid || (uint32_t(d.tid) == ptid && d.pos < ppos))) bad |= STATUS_UNSORTED;
     if (bad) atomicOr(&sc->status, bad);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// K2 filter + coordinate.  Four reads per thread with 128-bit loads and stores.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool keep_read(const FilterParams& p, uint32_t fm, int32_t tlen, int32_t* abs_tlen) {
-    const uint32_t flag = fm & 0xffffu, mapq = fm >> 16;
-    const int32_t a = tlen < 0 ? -tlen : tlen;   // abs() as the reference computes it (INT_MIN stays negative)
-    *abs_tlen = a;
-    bool keep = int32_t(mapq) >= p.mapqual;
-    keep = keep && !(p.required & ~flag);          // every required bit present   (src/bamsignals.cpp:21-23, :328)
-    keep = keep && (p.filtered & ~flag);           // not all filtered bits present (:329); filtered == 0 drops all
-    keep = keep && (!p.have_tlen || (a >= p.tmin && a <= p.tmax));
-    return keep;
-}
-
-template <bool COVERAGE>
-__global__ void __launch_bounds__(kThreads) k_filter(const int4* __restrict__ pos4, const int4* __restrict__ end4,
-                                                     const int4* __restrict__ tlen4, const uint4* __restrict__ fm4,
-                                                     int64_t row_lo, int64_t n, FilterParams p, int4* __restrict__ c0v,
-                                                     int4* __restrict__ c1v, DeviceScalars* sc) {
-    // rows [row_lo, n); the first quad may start below row_lo: those rows are recomputed (same values) but not counted
-    const int64_t q = (row_lo >> 2) + int64_t(blockIdx.x) * kThreads + threadIdx.x;
-    const int64_t n4 = (n + 3) >> 2;
-    int hlo = INT_MIN, hhi = INT_MIN, kept = 0;
-    if (q < n4) {
-        const int4 P = __ldg(pos4 + q), E = __ldg(end4 + q), T = __ldg(tlen4 + q);
-        const uint4 F = __ldg(fm4 + q);
-        const int32_t ps[4] = {P.x, P.y, P.z, P.w}, es[4] = {E.x, E.y, E.z, E.w}, ts[4] = {T.x, T.y, T.z, T.w};
-        const uint32_t fs[4] = {F.x, F.y, F.z, F.w};
-        int32_t o0[4], o1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int32_t a;
-            const bool keep = (4 * q + j < n) && keep_read(p, fs[j], ts[j], &a);
-            const bool neg = (fs[j] & 0x10u) != 0;
-            if (!COVERAGE) {
-                const int32_t offset = p.midpoint ? a / 2 + p.shift : p.shift;               // :339
-                const int32_t pos5 = neg ? es[j] - offset : ps[j] + offset;                  // :340-344
-                o0[j] = pos5;
-                o1[j] = keep ? int32_t(neg) : -1;
-                if (keep) { hlo = max(hlo, pos5 - ps[j]); hhi = max(hhi, ps[j] - pos5); }
-            } else {
-                int32_t s = ps[j], e = es[j];                                                 // :401-403
-                if (p.tspan) {
-                    if (neg && ts[j] < 0) s = e + ts[j] + 1;                                  // :408-409
-                    else if (!neg && ts[j] > 0) e = s + ts[j] - 1;                            // :410-411
-                }
-                o0[j] = keep ? s : INT_MAX;
-                o1[j] = keep ? e : INT_MIN;
-                if (keep) { hlo = max(hlo, e - ps[j]); hhi = max(hhi, ps[j] - s); }
-            }
-            kept += keep && (4 * q + j >= row_lo);
+    // Halo maxima and the kept-read count.  One redux per warp; the maxima go out only when they beat the value read at
+    // the start.  The count is summed per CTA in shared memory and the LAST warp to arrive publishes it (no block-level
+    // barrier: warps retire independently) into one of kKeptSlots counters that sit on different 128-byte lines -
+    // atomics on one line serialise in its L2 slice (measured: 1.8 M same-line atomics cost this kernel 3.7 ms).
+    hlo = __reduce_max_sync(FULL, hlo);
+    hhi = __reduce_max_sync(FULL, hhi);
+    const int kept = __popc(__ballot_sync(FULL, keep));
+    if (lane == 0) {
+        if (kept) {
+            if (hlo > s_ghlo) atomicMax(&sc->halo_lo, hlo);
+            if (hhi > s_ghhi) atomicMax(&sc->halo_hi, hhi);
+            atomicAdd(&s_kept, kept);
         }
-        c0v[q] = make_int4(o0[0], o0[1], o0[2], o0[3]);
-        c1v[q] = make_int4(o1[0], o1[1], o1[2], o1[3]);
-    }
-    __shared__ int s_lo[kThreads / 32], s_hi[kThreads / 32], s_k[kThreads / 32];
-    hlo = warp_max(hlo); hhi = warp_max(hhi); kept = warp_sum(kept);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { s_lo[wid] = hlo; s_hi[wid] = hhi; s_k[wid] = kept; }
-    __syncthreads();
-    if (wid == 0) {
-        hlo = lane < kThreads / 32 ? s_lo[lane] : INT_MIN;
-        hhi = lane < kThreads / 32 ? s_hi[lane] : INT_MIN;
-        kept = lane < kThreads / 32 ? s_k[lane] : 0;
-        hlo = warp_max(hlo); hhi = warp_max(hhi); kept = warp_sum(kept);
-        if (lane == 0) {
-            if (hlo > sc->halo_lo) atomicMax(&sc->halo_lo, hlo);
-            if (hhi > sc->halo_hi) atomicMax(&sc->halo_hi, hhi);
-            if (kept) atomicAdd(&sc->kept, (unsigned long long)kept);
+        __threadfence_block();
+        if (atomicAdd(&s_arrived, 1) == kThreads / 32 - 1) {
+            const int tot = *reinterpret_cast<volatile int*>(&s_kept);
+            if (tot) atomicAdd(&sc->kept[(blockIdx.x & (kKeptSlots - 1)) * kKeptStride], (unsigned long long)tot);
         }
     }
 }
@@ -342,11 +328,10 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic, uint32_
 
 // ---------------------------------------------------------------------------------------------------------------
 // K4 bamProfile: one CTA per tile (<= kTileInts output ints), shared-memory histogram.
-// AGG: the table is coordinate-sorted, so for binsize >> 1 consecutive lanes mostly fall into the same bin; runs
-// of equal bins inside a warp are detected with one shuffle + one ballot and collapsed to one shared atomic per
-// run (and per strand when ss), instead of one atomic per read.
+// k_profile: one read per lane and one shared atomic per counted read (binsize 1..3: neighbouring reads fall into
+// different bins anyway).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SS, bool BIN1, bool AGG>
+template <bool SS, bool BIN1>
 __global__ void __launch_bounds__(kThreads) k_profile(TileTable tiles, const int32_t* __restrict__ c0,
                                                       const int32_t* __restrict__ c1, int32_t binsize, uint64_t magic,
                                                       uint32_t mshift, int32_t* __restrict__ out) {
@@ -361,40 +346,85 @@ __global__ void __launch_bounds__(kThreads) k_profile(TileTable tiles, const int
     int32_t* hist = smem + (off & 3);                      // same 16-byte phase as the destination
     for (int k = threadIdx.x; k < nout; k += kThreads) hist[k] = 0;
     __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const int32_t p5 = __ldg(c0 + i), ng = __ldg(c1 + i);
+        int32_t rel = p5 - loc;
+        if (ng < 0 || uint32_t(rel) >= uint32_t(len)) continue;                    // src/bamsignals.cpp:351-353
+        const int a = (ng ^ flip) & 1;
+        if (flip) rel = len - 1 - rel;                                             // :356-359
+        const int32_t bin = BIN1 ? rel : int32_t(fast_div(uint32_t(rel), magic, mshift));
+        atomicAdd(&hist[SS ? 2 * bin + a : bin], 1);                               // :361-362
+    }
+    __syncthreads();
+    copy_out(out + off, hist, nout);
+}
+
+// k_profile_agg (binsize >= 4): the table is coordinate-sorted, so the reads a warp looks at fall into very few
+// bins (C4: 128 consecutive reads span ~400 bp of 200 bp bins).  Every lane takes FOUR consecutive reads (128-bit
+// loads) and folds them into one (key, count) pair; the warp then peels off its smallest key with redux.sync
+// (min over keys, add over the matching counts) and lane 0 issues ONE shared atomic per distinct key.  Three rounds
+// cover the common case (<= 3 distinct keys per warp); what is left goes out as one atomic per lane.
+// Division by binsize: exact for 0 <= n < 2^31 with a 32-bit multiplier m = ceil(2^(31+L) / d), L = ceil(log2 d):
+// n / d = umulhi(n, m) >> (L - 1).
+template <bool SS>
+__global__ void __launch_bounds__(kThreads) k_profile_agg(TileTable tiles, const int32_t* __restrict__ c0,
+                                                          const int32_t* __restrict__ c1, int32_t binsize, uint32_t magic,
+                                                          uint32_t mshift, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) int32_t smem[];
+    const int64_t tix = blockIdx.x;
+    const int32_t loc = tiles.loc[tix], len = tiles.len[tix];
+    const bool flip = tiles.strand[tix] < 0;
+    const int64_t lo = tiles.cand_lo[tix], hi = tiles.cand_hi[tix];
+    const int64_t off = tiles.out_off[tix];
+    const int nbins = int((uint32_t(len) + uint32_t(binsize) - 1u) / uint32_t(binsize));
+    const int nout = SS ? 2 * nbins : nbins;
+    int32_t* hist = smem + (off & 3);
+    for (int k = threadIdx.x; k < nout; k += kThreads) hist[k] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (int64_t base = lo + (threadIdx.x & ~31); base < hi; base += kThreads) {   // whole warps iterate together
-        const int64_t i = base + lane;
-        bool ok = false;
-        int32_t bin = -1, a = 0;
-        if (i < hi) {
-            const int32_t p5 = __ldg(c0 + i), ng = __ldg(c1 + i);
-            int32_t rel = p5 - loc;
-            ok = ng >= 0 && uint32_t(rel) < uint32_t(len);                         // src/bamsignals.cpp:351-353
-            a = (ng ^ flip) & 1;
-            if (flip) rel = len - 1 - rel;                                         // :356-359
-            if (ok) bin = BIN1 ? rel : int32_t(fast_div(uint32_t(rel), magic, mshift));
-        }
-        if (!AGG) {
-            if (ok) atomicAdd(&hist[SS ? 2 * bin + a : bin], 1);                   // :361-362
-        } else {
-            const int32_t prev = __shfl_up_sync(FULL, bin, 1);
-            const bool head = lane == 0 || bin != prev;
-            const uint32_t heads = __ballot_sync(FULL, head);
-            const uint32_t antis = __ballot_sync(FULL, a != 0);
-            if (ok && head) {
-                const uint32_t after = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-                const int next = after ? __ffs(after) - 1 : 32;
-                const uint32_t below_next = next == 32 ? FULL : ((1u << next) - 1u);
-                const uint32_t run = below_next & ~((1u << lane) - 1u);
-                if (SS) {
-                    const int ns = __popc(run & ~antis), na = __popc(run & antis);
-                    if (ns) atomicAdd(&hist[2 * bin], ns);
-                    if (na) atomicAdd(&hist[2 * bin + 1], na);
-                } else {
-                    atomicAdd(&hist[bin], __popc(run));
-                }
+    const int4* c0q = reinterpret_cast<const int4*>(c0);
+    const int4* c1q = reinterpret_cast<const int4*>(c1);
+    const int64_t q_lo = lo >> 2, q_hi = (hi + 3) >> 2;                            // quads of rows
+    for (int64_t qb = q_lo + (threadIdx.x & ~31); qb < q_hi; qb += kThreads) {     // whole warps iterate together
+        const int64_t q = qb + lane;
+        int key = INT_MAX, cnt = 0;
+        if (q < q_hi) {
+            const int4 P = __ldg(c0q + q);
+            int4 N = __ldg(c1q + q);
+            if (4 * q < lo || 4 * q + 4 > hi) {                                    // first / last quad of the range
+                const int64_t r0 = 4 * q;
+                if (r0 < lo || r0 >= hi) N.x = -1;
+                if (r0 + 1 < lo || r0 + 1 >= hi) N.y = -1;
+                if (r0 + 2 < lo || r0 + 2 >= hi) N.z = -1;
+                if (r0 + 3 < lo || r0 + 3 >= hi) N.w = -1;
             }
+            const int32_t ps[4] = {P.x, P.y, P.z, P.w}, ns[4] = {N.x, N.y, N.z, N.w};
+            int k[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int32_t r = ps[j] - loc;
+                const bool ok = ns[j] >= 0 && uint32_t(r) < uint32_t(len);         // src/bamsignals.cpp:351-353
+                const int32_t rel = flip ? len - 1 - r : r;                        // :356-359
+                const int32_t bin = int32_t(__umulhi(uint32_t(rel), magic) >> mshift);
+                const int kk = SS ? 2 * bin + ((ns[j] ^ int(flip)) & 1) : bin;     // :361-362
+                k[j] = ok ? kk : INT_MAX;
+            }
+            key = min(min(k[0], k[1]), min(k[2], k[3]));
+            cnt = int(k[0] == key) + int(k[1] == key) + int(k[2] == key) + int(k[3] == key);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k[j] != key && k[j] != INT_MAX) atomicAdd(&hist[k[j]], 1);
         }
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+            const int kmin = __reduce_min_sync(FULL, key);
+            if (kmin == INT_MAX) break;                                            // warp-uniform
+            const bool mine = key == kmin;
+            const int tot = __reduce_add_sync(FULL, mine ? cnt : 0);
+            if (lane == 0) atomicAdd(&hist[kmin], tot);
+            if (mine) key = INT_MAX;
+        }
+        if (key != INT_MAX) atomicAdd(&hist[key], cnt);
     }
     __syncthreads();
     copy_out(out + off, hist, nout);
@@ -475,32 +505,20 @@ void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
 
 }  // namespace
 
-void launch_decode(const DecodeBatch& one, ReadTable t, DeviceScalars* sc, cudaStream_t s) {
+void launch_decode(const DecodeBatch& one, ReadTable t, bool coverage, const FilterParams& p, DeviceScalars* sc, cudaStream_t s) {
     if (one.n <= 0) return;
     const int grid = (one.n + kThreads - 1) / kThreads;
     DecodeBatch b = one;
     b.chunk0 = 0;
-    k_decode<<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, sc);
+    if (coverage) k_decode<true><<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
+    else k_decode<false><<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
 }
 
-void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, DeviceScalars* sc,
-                         cudaStream_t s) {
+void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, bool coverage,
+                         const FilterParams& p, DeviceScalars* sc, cudaStream_t s) {
     if (n_batches <= 0 || total_chunks <= 0) return;
-    k_decode<<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, sc);
-}
-
-void launch_filter_pileup(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
-    if (n <= row_lo) return;
-    const int64_t n4 = (n + 3) / 4 - (row_lo >> 2), grid = (n4 + kThreads - 1) / kThreads;
-    k_filter<false><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
-                                                        (const uint4*)t.flagmq, row_lo, n, p, (int4*)c0, (int4*)c1, sc);
-}
-
-void launch_filter_coverage(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s) {
-    if (n <= row_lo) return;
-    const int64_t n4 = (n + 3) / 4 - (row_lo >> 2), grid = (n4 + kThreads - 1) / kThreads;
-    k_filter<true><<<unsigned(grid), kThreads, 0, s>>>((const int4*)t.pos, (const int4*)t.end, (const int4*)t.tlen,
-                                                       (const uint4*)t.flagmq, row_lo, n, p, (int4*)c0, (int4*)c1, sc);
+    if (coverage) k_decode<true><<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
+    else k_decode<false><<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
 }
 
 void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s) {
@@ -519,16 +537,21 @@ void launch_count(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int
 void launch_profile(TileTable tiles, int64_t n_tiles, const int32_t* c0, const int32_t* c1, int ss, int32_t binsize,
                     int max_tile_ints, int32_t* out, DeviceScalars*, cudaStream_t s) {
     if (n_tiles <= 0) return;
-    uint64_t magic; uint32_t mshift;
-    magic_for(binsize, &magic, &mshift);
     const size_t smem = size_t(max_tile_ints + 4) * sizeof(int32_t);
     const unsigned grid = unsigned(n_tiles);
-    const bool agg = binsize >= 4;
-#define BSG_LAUNCH_PROFILE(SS, B1, AG) \
-    k_profile<SS, B1, AG><<<grid, kThreads, smem, s>>>(tiles, c0, c1, binsize, magic, mshift, out)
-    if (binsize == 1) { if (ss) BSG_LAUNCH_PROFILE(true, true, false); else BSG_LAUNCH_PROFILE(false, true, false); }
-    else if (agg)     { if (ss) BSG_LAUNCH_PROFILE(true, false, true); else BSG_LAUNCH_PROFILE(false, false, true); }
-    else              { if (ss) BSG_LAUNCH_PROFILE(true, false, false); else BSG_LAUNCH_PROFILE(false, false, false); }
+    if (binsize >= 4) {
+        uint32_t L = 0;
+        while ((1ull << L) < uint64_t(binsize)) ++L;
+        const uint32_t magic = uint32_t(((1ull << (31 + L)) + uint64_t(binsize) - 1) / uint64_t(binsize));
+        if (ss) k_profile_agg<true><<<grid, kThreads, smem, s>>>(tiles, c0, c1, binsize, magic, L - 1, out);
+        else k_profile_agg<false><<<grid, kThreads, smem, s>>>(tiles, c0, c1, binsize, magic, L - 1, out);
+        return;
+    }
+    uint64_t magic; uint32_t mshift;
+    magic_for(binsize, &magic, &mshift);
+#define BSG_LAUNCH_PROFILE(SS, B1) k_profile<SS, B1><<<grid, kThreads, smem, s>>>(tiles, c0, c1, binsize, magic, mshift, out)
+    if (binsize == 1) { if (ss) BSG_LAUNCH_PROFILE(true, true); else BSG_LAUNCH_PROFILE(false, true); }
+    else              { if (ss) BSG_LAUNCH_PROFILE(true, false); else BSG_LAUNCH_PROFILE(false, false); }
 #undef BSG_LAUNCH_PROFILE
 }
 

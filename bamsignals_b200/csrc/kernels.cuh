@@ -3,10 +3,10 @@
 // HBM layout (all arrays cudaMalloc-aligned, SoA so that every kernel's loads and stores are coalesced):
 //   raw batch      uint8  raw[]         uncompressed BAM record bytes of one staged batch (+16 B slack)
 //                  uint32 offs[n+1]     byte offset of every record's block_size field; offs[n] = end of last record
-//   read table     int32  tid[N] pos[N] end[N] tlen[N], uint32 flagmq[N]   (20 B / read; end = 0-based inclusive
-//                                       alignment end = bam_endpos - 1; flagmq = flag | mapq << 16)
-//   coordinates    int32  c0[N] c1[N]   (8 B / read) pileup: c0 = 5'/midpoint coordinate, c1 = 0 '+', 1 '-', -1 dropped
+//   read table     int32  tid[N] pos[N]  (8 B / read) the join key: rows are in file order = sorted by (tid, pos)
+//                  int32  c0[N] c1[N]    (8 B / read) pileup: c0 = 5'/midpoint coordinate, c1 = 0 '+', 1 '-', -1 dropped
 //                                       coverage: [c0,c1] = inclusive interval, dropped reads get c0 > c1 sentinels
+//                                       (end, tlen, flag and mapq never leave the decode kernel's registers)
 //   tiles          int32  rid loc len strand, int64 out_off, int64 cand_lo cand_hi   one row per region tile
 //   result         int32  out[]         flat, bsg_output_layout() order; every element written exactly once
 #pragma once
@@ -18,9 +18,8 @@ namespace bsg {
 struct ReadTable {
     int32_t* tid;
     int32_t* pos;
-    int32_t* end;
-    int32_t* tlen;
-    uint32_t* flagmq;
+    int32_t* c0;
+    int32_t* c1;
 };
 
 struct TileTable {
@@ -48,9 +47,11 @@ struct DeviceScalars {
     int32_t halo_hi;     // pileup: max(pos - c0);                coverage: max(pos - c0)
     uint32_t status;     // bit 0: unsorted input, bit 1: corrupt record
     uint32_t pad;
-    unsigned long long kept;
     unsigned long long candidates;
-};
+    unsigned long long pad2[13];           // the counters below start on a 128-byte line
+    unsigned long long kept[32 * 16];      // partial counts of reads that passed the filter: CTA i adds to slot i % 32,
+};                                         // slots are 128 bytes apart (one L2 line each); the host sums them
+constexpr int kKeptSlots = 32, kKeptStride = 16;
 enum : uint32_t { STATUS_UNSORTED = 1u, STATUS_CORRUPT = 2u, STATUS_BAD_DEFLATE = 4u, STATUS_BAD_CRC = 8u };
 
 constexpr int kTileInts = 8192;   // int32 per counting tile (32 KiB of shared memory)
@@ -65,12 +66,13 @@ struct DecodeBatch {
 };
 constexpr int kDecodeChunk = 256;
 
-// K1: raw record bytes -> read table rows [row0, row0 + n).  Replaces bam_read1's field extraction and
-// bam_endpos (src/bamsignals.cpp:16-18).  launch_decode: one batch (streaming path); launch_decode_table: every
-// resident batch of a staged session in ONE launch (d_table lives in device memory).
-void launch_decode(const DecodeBatch& one, ReadTable t, DeviceScalars* sc, cudaStream_t s);
-void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, DeviceScalars* sc,
-                         cudaStream_t s);
+// K1 (decode + filter, fused): raw record bytes -> read table rows [row0, row0 + n).  Replaces bam_read1's field
+// extraction, bam_endpos (src/bamsignals.cpp:16-18) and setRead (:326-346 pileup, :392-415 coverage).
+// launch_decode: one batch (streaming path); launch_decode_table: every resident batch of a staged session in ONE
+// launch (d_table lives in device memory).
+void launch_decode(const DecodeBatch& one, ReadTable t, bool coverage, const FilterParams& p, DeviceScalars* sc, cudaStream_t s);
+void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, bool coverage,
+                         const FilterParams& p, DeviceScalars* sc, cudaStream_t s);
 
 // K0 (gpu_inflate): one BGZF block = one raw-DEFLATE stream of at most 64 KiB.
 struct InflateBlock {
@@ -88,10 +90,6 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
 // (count, scan, write) fill d_offs[0..total] (+ end sentinel) and *d_total.
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
                  uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
-
-// K2: filter + coordinate (setRead, src/bamsignals.cpp:326-346 and :392-415) for table rows [row_lo, n).
-void launch_filter_pileup(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
-void launch_filter_coverage(ReadTable t, int64_t row_lo, int64_t n, FilterParams p, int32_t* c0, int32_t* c1, DeviceScalars* sc, cudaStream_t s);
 
 // K3: per tile, binary-search the (tid,pos)-sorted table for the candidate row range (the job of the sort + chunk
 // + sweep in overlapAndPileup, src/bamsignals.cpp:246-285).

@@ -6,7 +6,7 @@ windows on a synthetic 100M-read single-end BAM), B200 path vs the reference CPU
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the counting hot path over the whole workload:
   value  kernel-only: raw record bytes + record offsets already resident in HBM (bsg_stage), the step runs
-         K1 decode -> K2 filter -> K3 join -> K4/K5 count on the device; timed with CUDA events on the library's
+         K1 decode+filter -> K3 join -> K4/K5 count on the device; timed with CUDA events on the library's
          compute stream (first event to last event of every step, summed), max over ranks.
   e2e    the same metric through the reference-facing C-ABI call (bsg_pileup / bsg_coverage) from the BAM *file*
          (page cache) to the result in host memory: BAI query, inflate, record walk, H2D, kernels, D2H all inside.
@@ -34,10 +34,11 @@ for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
 import workloads as WL  # noqa: E402
 
 FULL_READS = {"c2": 100e6, "c3": 2 * 24895642, "c4": 1e9, "c5": 500e6}
-# algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md): K1 4+36+4*n_cigar+20 (n_cigar ~ 1.15 on the synthetic mix),
-# K2 20+8, K3 24 per tile, K4/K5 8*C + 4*B.
-K1_BYTES_PER_READ = 4 + 36 + 4 * 1.18 + 20
-K2_BYTES_PER_READ = 28
+# algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md): K1 (decode + filter fused: the 20-byte table row of SURVEY 8d
+# never leaves registers) 4 + 36 + 4*n_cigar in, 16 out (tid, pos, c0, c1); n_cigar ~ 1.18 on the synthetic mix.
+# K3 24 per tile, K4/K5 8*C + 4*B.
+K1_BYTES_PER_READ = 4 + 36 + 4 * 1.18 + 16
+K2_BYTES_PER_READ = 0
 
 
 def data_dir():
@@ -165,7 +166,10 @@ def run_ours(args, rank, world, local_rank):
         te = B.timings()
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
-    h2d = te["bytes_inflated"] + 4 * (te["records"] + te["n_batches"]) + 28 * te["n_tiles"]
+    if gpu_inflate > 0:     # compressed bytes + block descriptors (16 B + 4 B CRC per <= 64 KiB block) + tiles
+        h2d = te["bytes_compressed"] + 20 * (te["bytes_inflated"] // 65280 + 1) + 24 * te["n_tiles"]
+    else:                   # inflated bytes + record offsets + tiles
+        h2d = te["bytes_inflated"] + 4 * (te["records"] + te["n_batches"]) + 24 * te["n_tiles"]
     d2h = 4 * te["out_elems"]
     del res
 

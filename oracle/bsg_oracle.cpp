@@ -208,38 +208,93 @@ bool next_record(BgzfIn& in, std::vector<uint8_t>& buf, Rec& r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// BAI index and the htslib-style region query
+// BAI / CSI index and the htslib-style region query
 // ---------------------------------------------------------------------------------------------
 struct Chunk { uint64_t beg, end; };
-struct RefIndex { std::unordered_map<uint32_t, std::vector<Chunk>> bins; std::vector<uint64_t> linear; };
-struct Bai { std::vector<RefIndex> refs; };
+struct RefIndex {
+    std::unordered_map<uint32_t, std::vector<Chunk>> bins;
+    std::unordered_map<uint32_t, uint64_t> loff;    // CSI only: per-bin "loffset"
+    std::vector<uint64_t> linear;                    // BAI only
+};
+struct Bai {                                         // a BAI (min_shift 14, depth 5) or a CSI index
+    std::vector<RefIndex> refs;
+    int min_shift = 14, depth = 5;
+    bool csi = false;
+};
 
-Bai load_bai(const std::string& bampath) {
-    std::string cand[2] = {bampath + ".bai", bampath};
-    if (bampath.size() > 4 && bampath.compare(bampath.size() - 4, 4, ".bam") == 0)
-        cand[1] = bampath.substr(0, bampath.size() - 4) + ".bai";
-    FILE* fp = nullptr;
-    for (auto& c : cand) { if (c == bampath) continue; fp = fopen(c.c_str(), "rb"); if (fp) break; }
-    if (!fp) fail("BAM indexing file is not available for file " + bampath);   // src/bamsignals.cpp:209
+// A .csi file is BGZF-compressed; a .bai is not.
+std::vector<uint8_t> read_maybe_bgzf(FILE* fp) {
     std::vector<uint8_t> d;
     uint8_t tmp[65536]; size_t k;
     while ((k = fread(tmp, 1, sizeof tmp, fp)) > 0) d.insert(d.end(), tmp, tmp + k);
+    if (d.size() < 18 || d[0] != 0x1f || d[1] != 0x8b) return d;
+    std::vector<uint8_t> out;
+    size_t p = 0;
+    while (p + 18 <= d.size()) {
+        const uint8_t* h = d.data() + p;
+        if (h[0] != 0x1f || h[1] != 0x8b) fail("bad BGZF header in index");
+        const uint32_t xlen = h[10] | h[11] << 8;
+        const uint32_t bsize = (h[16] | h[17] << 8) + 1u;        // htslib writes BC first with XLEN 6
+        if (xlen != 6 || h[12] != 'B' || h[13] != 'C' || p + bsize > d.size()) fail("unsupported BGZF layout in index");
+        uint32_t isize; memcpy(&isize, h + bsize - 4, 4);
+        const size_t old = out.size();
+        out.resize(old + isize);
+        if (isize) {
+            z_stream zs; memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) fail("zlib init failed");
+            zs.next_in = const_cast<Bytef*>(h + 18); zs.avail_in = bsize - 18 - 8;
+            zs.next_out = out.data() + old; zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out) fail("index inflate failed");
+        }
+        p += bsize;
+    }
+    return out;
+}
+
+// htslib looks for <bam>.csi, then <bam minus extension>.csi, then the same two with .bai (hts_idx_load, HTS_FMT_BAI)
+Bai load_bai(const std::string& bampath) {
+    std::vector<std::string> cand = {bampath + ".csi"};
+    const bool ext = bampath.size() > 4 && bampath.compare(bampath.size() - 4, 4, ".bam") == 0;
+    if (ext) cand.push_back(bampath.substr(0, bampath.size() - 4) + ".csi");
+    cand.push_back(bampath + ".bai");
+    if (ext) cand.push_back(bampath.substr(0, bampath.size() - 4) + ".bai");
+    FILE* fp = nullptr;
+    for (auto& c : cand) { fp = fopen(c.c_str(), "rb"); if (fp) break; }
+    if (!fp) fail("BAM indexing file is not available for file " + bampath);   // src/bamsignals.cpp:209
+    std::vector<uint8_t> d = read_maybe_bgzf(fp);
     fclose(fp);
     size_t p = 0;
-    auto need = [&](size_t n) { if (p + n > d.size()) fail("truncated BAI index"); };
+    auto need = [&](size_t n) { if (p + n > d.size()) fail("truncated BAM index"); };
     need(8);
-    if (memcmp(d.data(), "BAI\1", 4) != 0) fail("bad BAI magic");
-    int32_t n_ref = rd_i32(d.data() + 4); p = 8;
-    Bai bai; bai.refs.resize(n_ref);
+    Bai bai;
+    if (memcmp(d.data(), "CSI\1", 4) == 0) {            // CSIv1: magic, min_shift, depth, l_aux, aux, n_ref
+        bai.csi = true;
+        need(16);
+        bai.min_shift = rd_i32(d.data() + 4); bai.depth = rd_i32(d.data() + 8);
+        const int32_t l_aux = rd_i32(d.data() + 12);
+        p = 16; need(size_t(l_aux) + 4); p += l_aux;
+        if (bai.min_shift < 1 || bai.depth < 1 || bai.min_shift + 3 * bai.depth > 40) fail("unsupported CSI geometry");
+    } else {
+        if (memcmp(d.data(), "BAI\1", 4) != 0) fail("bad BAI magic");
+        p = 4;
+    }
+    int32_t n_ref = rd_i32(d.data() + p); p += 4;
+    bai.refs.resize(n_ref);
     for (int r = 0; r < n_ref; ++r) {
         need(4); int32_t n_bin = rd_i32(d.data() + p); p += 4;
         for (int b = 0; b < n_bin; ++b) {
-            need(8); uint32_t bin = rd_u32(d.data() + p); int32_t n_chunk = rd_i32(d.data() + p + 4); p += 8;
+            need(bai.csi ? 16 : 8);
+            uint32_t bin = rd_u32(d.data() + p); p += 4;
+            if (bai.csi) { uint64_t lo; memcpy(&lo, d.data() + p, 8); p += 8; bai.refs[r].loff[bin] = lo; }
+            int32_t n_chunk = rd_i32(d.data() + p); p += 4;
             need(16ull * n_chunk);
             std::vector<Chunk> cs(n_chunk);
             for (int c = 0; c < n_chunk; ++c) { memcpy(&cs[c].beg, d.data() + p, 8); memcpy(&cs[c].end, d.data() + p + 8, 8); p += 16; }
             bai.refs[r].bins[bin] = std::move(cs);
         }
+        if (bai.csi) continue;
         need(4); int32_t n_intv = rd_i32(d.data() + p); p += 4;
         need(8ull * n_intv);
         bai.refs[r].linear.resize(n_intv);
@@ -249,15 +304,17 @@ Bai load_bai(const std::string& bampath) {
     return bai;
 }
 
-// UCSC binning scheme (SAM spec section 5.3): bins that may hold records overlapping [beg,end)
-void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t>& out) {
+// Binning scheme (SAM spec section 5.3, generalised in CSIv1): bins that may hold records overlapping [beg,end).
+// Level l has 8^l bins of 2^(min_shift + 3 (depth - l)) bp; its first bin number is (8^l - 1) / 7.
+void reg2bins(int64_t beg, int64_t end, int min_shift, int depth, std::vector<uint32_t>& out) {
     out.clear();
     if (beg >= end) return;
-    if (end > (1LL << 29)) end = 1LL << 29;
+    const int64_t maxpos = 1LL << (min_shift + 3 * depth);
+    if (end > maxpos) end = maxpos;
+    if (beg >= end) return;
     --end;
-    out.push_back(0);
-    for (int shift = 26, t = 1; shift >= 14; shift -= 3, t = (t << 3) + 1)   // level offsets 1, 9, 73, 585, 4681
-        for (int64_t k = t + (beg >> shift); k <= t + (end >> shift); ++k) out.push_back(uint32_t(k));
+    for (int l = 0, t = 0, s = min_shift + 3 * depth; l <= depth; s -= 3, t += 1 << (3 * l), ++l)
+        for (int64_t k = t + (beg >> s); k <= t + (end >> s); ++k) out.push_back(uint32_t(k));
 }
 
 std::vector<Chunk> query_chunks(const Bai& bai, int tid, int64_t beg, int64_t end) {
@@ -267,11 +324,24 @@ std::vector<Chunk> query_chunks(const Bai& bai, int tid, int64_t beg, int64_t en
     if (beg < 0) beg = 0;
     if (end <= beg) return res;
     uint64_t min_off = 0;
-    if (!ri.linear.empty()) {
-        size_t w = size_t(beg >> 14);
-        min_off = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
+    if (!bai.csi) {
+        if (!ri.linear.empty()) {
+            size_t w = size_t(beg >> 14);
+            min_off = w < ri.linear.size() ? ri.linear[w] : ri.linear.back();
+        }
+    } else {
+        // htslib's hts_itr_query: the loffset of the leaf bin holding `beg`; if that bin does not exist, of the nearest
+        // existing bin to its left on the same level below the same parent, else of the parent, and so on up to bin 0
+        uint32_t bin = uint32_t(((1ull << (3 * bai.depth)) - 1) / 7 + (uint64_t(beg) >> bai.min_shift));
+        for (;;) {
+            auto it = ri.loff.find(bin);
+            if (it != ri.loff.end()) { min_off = it->second; break; }
+            if (bin == 0) break;
+            const uint32_t parent = (bin - 1) >> 3, first = (parent << 3) + 1;
+            bin = bin > first ? bin - 1 : parent;
+        }
     }
-    std::vector<uint32_t> bins; reg2bins(beg, end, bins);
+    std::vector<uint32_t> bins; reg2bins(beg, end, bai.min_shift, bai.depth, bins);
     for (uint32_t b : bins) {
         auto it = ri.bins.find(b);
         if (it == ri.bins.end()) continue;

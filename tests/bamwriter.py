@@ -41,7 +41,7 @@ def record_bytes(tid, pos, flag, mapq, cigar, tlen, name="r", l_seq=0, aux=b"", 
     rl = ref_len(ops, flag) or 1
     nm = name.encode() + b"\0"
     n_cig = len(ops)
-    body = struct.pack("<iiBBHHHiiii", tid, pos, len(nm), mapq, reg2bin(pos, pos + rl) if pos >= 0 else 4680,
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(nm), mapq, (reg2bin(pos, pos + rl) & 0xFFFF) if pos >= 0 else 4680,
                        n_cig & 0xFFFF, flag, l_seq, next_tid, next_pos, tlen)
     body += nm + b"".join(struct.pack("<I", n << 4 | op) for n, op in ops)
     body += bytes((l_seq + 1) // 2) + bytes([30] * l_seq) + aux
@@ -58,10 +58,33 @@ def bgzf_block(data, level=6):
 EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def write_bam(path, refs, reads, block_payload=0xFF00, cut_mid_record=False, write_index=True, level=6):
+def reg2bin_csi(beg, end, min_shift, depth):
+    """CSIv1 reg2bin: the smallest bin that contains [beg, end)."""
+    end -= 1
+    s, t = min_shift, ((1 << depth * 3) - 1) // 7
+    for l in range(depth, 0, -1):
+        if beg >> s == end >> s:
+            return t + (beg >> s)
+        s += 3
+        t -= 1 << ((l - 1) * 3)
+    return 0
+
+
+def bin_first_window(b, depth):
+    """First leaf-level window a bin covers (htslib's hts_bin_bot)."""
+    l, first = 0, 0
+    while l < depth and b >= first + (1 << 3 * l):
+        first += 1 << 3 * l
+        l += 1
+    return (b - first) << (3 * (depth - l))
+
+
+def write_bam(path, refs, reads, block_payload=0xFF00, cut_mid_record=False, write_index=True, level=6,
+              index="bai", min_shift=14, depth=5):
     """refs: [(name, length)]; reads: dicts(tid,pos,flag,mapq,cigar,tlen[,name,l_seq,aux]) in file order.
     block_payload: uncompressed bytes per BGZF block; cut_mid_record: blocks are cut at exactly block_payload bytes
-    (records straddle), otherwise at record boundaries like htslib."""
+    (records straddle), otherwise at record boundaries like htslib.
+    index: "bai" (<path>.bai), "csi" (<path>.csi, BGZF-compressed CSIv1 with the given min_shift / depth) or "both"."""
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
     hdr = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs))
     for n, l in refs:
@@ -107,6 +130,10 @@ def write_bam(path, refs, reads, block_payload=0xFF00, cut_mid_record=False, wri
             return cstart[-1] << 16
         return cstart[k] << 16 | (u - cuts[k])
 
+    if index in ("csi", "both"):
+        _write_csi(path + ".csi", refs, recs, voff, min_shift, depth, level)
+        if index == "csi":
+            return
     idx = [dict(bins={}, lin={}, beg=None, end=None, nm=0, nu=0) for _ in refs]
     cur = (None, None)
     run = None
@@ -154,3 +181,54 @@ def write_bam(path, refs, reads, block_payload=0xFF00, cut_mid_record=False, wri
         bai += struct.pack("<i", n_intv) + b"".join(struct.pack("<Q", v) for v in lin)
     bai += struct.pack("<Q", n_no_coor)
     open(path + ".bai", "wb").write(bai)
+
+
+def _write_csi(path, refs, recs, voff, min_shift, depth, level=6):
+    """CSIv1 (SAM spec CSIv1.pdf): magic, min_shift, depth, l_aux = 0, n_ref, then per reference the bins with their
+    loffset (= linear-index entry of the bin's first window, as htslib's update_loff derives it) and chunks, plus the
+    pseudo-bin; the whole file BGZF-compressed."""
+    meta = ((1 << (depth + 1) * 3) - 1) // 7 + 1
+    idx = [dict(bins={}, lin={}, beg=None, end=None, nm=0, nu=0) for _ in refs]
+    cur, run, n_no_coor = (None, None), None, 0
+    for off, ln, tid, pos, end, flag in recs:
+        if tid < 0:
+            n_no_coor += 1
+            continue
+        vb, ve = voff(off), voff(off + ln)
+        ri = idx[tid]
+        b = reg2bin_csi(pos, end, min_shift, depth)
+        if (tid, b) != cur:
+            if run:
+                idx[run[0]]["bins"].setdefault(run[1], []).append((run[2], run[3]))
+            cur, run = (tid, b), [tid, b, vb, ve]
+        else:
+            run[3] = ve
+        for w in range(pos >> min_shift, ((end - 1) >> min_shift) + 1):
+            ri["lin"].setdefault(w, vb)
+        ri["beg"] = vb if ri["beg"] is None else ri["beg"]
+        ri["end"] = ve
+        ri["nu" if flag & 4 else "nm"] += 1
+    if run:
+        idx[run[0]]["bins"].setdefault(run[1], []).append((run[2], run[3]))
+    body = bytearray(b"CSI\1" + struct.pack("<iiii", min_shift, depth, 0, len(refs)))
+    for ri in idx:
+        n_intv = (max(ri["lin"]) + 1) if ri["lin"] else 0
+        lin, prev = [], ri["beg"] or 0          # leading gaps take the reference's first offset, later ones the previous entry
+        for w in range(n_intv):
+            prev = ri["lin"].get(w, prev)
+            lin.append(prev)
+        nb = len(ri["bins"]) + (1 if ri["beg"] is not None else 0)
+        body += struct.pack("<i", nb)
+        for b, chunks in sorted(ri["bins"].items()):
+            w = bin_first_window(b, depth)
+            body += struct.pack("<IQi", b, lin[w] if w < n_intv else 0, len(chunks))
+            for c in chunks:
+                body += struct.pack("<QQ", *c)
+        if ri["beg"] is not None:
+            body += struct.pack("<IQiQQQQ", meta, 0, 2, ri["beg"], ri["end"], ri["nm"], ri["nu"])
+    body += struct.pack("<Q", n_no_coor)
+    out = bytearray()
+    for a in range(0, len(body), 0xFF00):
+        out += bgzf_block(bytes(body[a:a + 0xFF00]), level)
+    out += EOF_BLOCK
+    open(path, "wb").write(out)

@@ -12,11 +12,12 @@
 
 using namespace bsg::inflate_core;
 
-static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, uint8_t* out, uint32_t out_len) {
     static Tables T;
     static uint32_t q[kQueue];
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(buf);      // the whole file, 4-byte aligned
     BitReader br;
-    br.init(in);
+    br.init(base, in_off);
     uint32_t op_dec = 0, pos_base = 0;
     int phase = 0, last = 0, bad = 0;
     for (;;) {
@@ -30,12 +31,10 @@ static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint3
                 br.consume(32);
                 const uint32_t len = v & 0xffffu, nlen = v >> 16;
                 if ((len ^ nlen) != 0xffffu || op_dec + len > out_len) return 3;
-                const uint8_t* src = br.byte_ptr();
-                memcpy(out + op_dec, src, len);
+                const uint32_t src_off = br.byte_pos();
+                memcpy(out + op_dec, buf + src_off, len);
                 op_dec += len;
-                const uint64_t used = br.bits_used() + uint64_t(len) * 8;
-                (void)used;
-                br.init(src + len);
+                br.init(base, src_off + len);
                 q[0] = kTokSkip | len;
                 nq = 1;
                 if (last) done = 1;
@@ -43,7 +42,7 @@ static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint3
         }
         if (phase == 1 && nq == 0) {
             int eob = 0;
-            nq = fill_queue(br, T, q, &op_dec, &eob, &bad);
+            nq = fill_queue(br, ArrayAccess{&T, q}, &op_dec, &eob, &bad);
             if (eob) { phase = 0; if (last) done = 1; }
             if (bad || op_dec > out_len) return 4;
         }
@@ -119,7 +118,7 @@ static int inflate_block(const uint8_t* in, uint32_t in_len, uint8_t* out, uint3
         if (done) break;
     }
     if (op_dec != out_len || pos_base != out_len) return 5;
-    if (br.bits_used() > uint64_t(in_len) * 8) return 6;
+    if (br.bit_pos() > (uint64_t(in_off) + in_len) * 8) return 6;
     return 0;
 }
 
@@ -143,7 +142,7 @@ int main(int argc, char** argv) {
         memcpy(&isize, h + bs - 4, 4);
         memcpy(&crc, h + bs - 8, 4);
         std::vector<uint8_t> out(isize + 64);
-        const int rc = inflate_block(h + 12 + xlen, bs - 12 - xlen - 8, out.data(), isize);
+        const int rc = inflate_block(d.data(), uint32_t(off + 12 + xlen), bs - 12 - xlen - 8, out.data(), isize);
         if (rc || uint32_t(crc32(crc32(0, nullptr, 0), out.data(), isize)) != crc) {
             if (++bad < 5) fprintf(stderr, "block %d at %zu: rc %d\n", nb, off, rc);
         }

@@ -148,7 +148,7 @@ def test_staged_session_matches(fixture_bam):
             flat = st.pileup((0, 1000), 5, binsize, shift, ss, 66, 1024, True)
             want = O.pileup_core(fixture_bam, gr, (0, 1000), 5, binsize, shift, bool(ss), 66, 1024, True)
             assert np.array_equal(flat, np.concatenate([w.ravel(order="F") for w in want]))
-            assert B.timings()["ms_device"] > 0 and B.timings()["n_launches"] >= 4
+            assert B.timings()["ms_device"] > 0 and B.timings()["n_launches"] >= 3   # decode+filter, join, count
         flat = st.coverage((0, 1000), 0, 66, -1, True)
         assert np.array_equal(flat, np.concatenate(O.coverage_core(fixture_bam, gr, (0, 1000), 0, 66, -1, True)))
         assert st.pileup(None, want_output=False) is None

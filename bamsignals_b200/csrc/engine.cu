@@ -273,10 +273,13 @@ public:
         for (size_t i = 0; i < segs_.size();) {
             auto b = std::make_unique<Batch>();
             b->seg_first = i;
-            // (Measured: batches well below 1 GiB leave the inflate kernel, one warp per BGZF block, with fewer blocks
-            // than the 148 x 28 warps the GPU holds - a 128 MiB ... 1 GiB ramp cost C2 30 ms end to end.)
+            // (Measured: batches well below 1 GiB leave the inflate kernel with fewer BGZF blocks than the 148 x 56
+            // streams the GPU holds - a 128 MiB ... 1 GiB ramp cost C2 30 ms end to end.)  Only the FIRST batch is
+            // short: nothing overlaps its upload, so the device starts after a quarter of the usual copy.
+            const bool first_short = gpu && !keep_raw && opts_.batch_bytes <= 0 && i == 0 && !getenv("BSG_NO_SHORT_FIRST");
+            const uint64_t limit = first_short ? uint64_t(batch_bytes) / 4 : uint64_t(batch_bytes);
             uint64_t acc = 0;
-            while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= uint64_t(batch_bytes))) {
+            while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= limit)) {
                 acc += (segs_[i].usize + 15) & ~15ull;
                 ++i;
             }
@@ -858,6 +861,7 @@ private:
                 if (n > 0 && cnt_.active) {
                     // (tid, pos) of the last decoded record = how far the sorted read stream has come: count + ship
                     // every tile it finalises while the next batch inflates
+                    // (Polling for the frontier between upload chunks instead of blocking here was measured: no gain.)
                     ReadTable t = table();
                     int32_t* f = c.h_front.as<int32_t>();
                     BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
@@ -916,7 +920,12 @@ private:
             const uint32_t end_pos = walkers.empty() ? 0u : walkers.back().y;
             t_desc += now_ms() - tt; tt = now_ms();
             // ---- buffers ------------------------------------------------------------------------------------------------
-            BSG_CUDA(cudaEventSynchronize(c.ev_gfree[slot]));          // K1 of the batch that used this slot is done
+            // The upload overwrites only the compressed bytes and the descriptor arrays of this slot; their readers are
+            // the inflate, walk and CRC kernels of the batch before last.  The slot's RAW buffer is still being read by
+            // that batch's decode kernel, but it is written next by this batch's inflate: a device-side dependency
+            // (stream wait below), not a reason to hold the upload back.
+            BSG_CUDA(cudaEventSynchronize(c.ev_total[slot]));
+            BSG_CUDA(cudaEventSynchronize(c.ev_crc[slot]));
             t_wait += now_ms() - tt; tt = now_ms();
             c.g_comp[slot].ensure(cbase + 4096);   // slack: the bit reader looks ahead, and a corrupt stream may run on for one round
             c.g_blocks[slot].ensure(blocks.size() * sizeof(InflateBlock) + 64);
@@ -981,6 +990,7 @@ private:
             t_copy += now_ms() - tt; tt = now_ms();
             // ---- device: inflate -> walk -> total ------------------------------------------------------------------------------
             BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
+            BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_gfree[slot], 0));       // decode (+ CRC) of the slot's previous batch
             Span sp{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
             launch_inflate(c.g_blocks[slot].as<InflateBlock>(), int(blocks.size()), c.g_comp[slot].as<uint8_t>(), d_raw,

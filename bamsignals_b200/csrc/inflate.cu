@@ -2,10 +2,10 @@
 // file and ships COMPRESSED bytes; raw-DEFLATE decoding of every BGZF block, its integrity check and the block_size
 // chain walk run on the device.
 //
-// k_inflate_q2: one warp per BGZF block (RFC 1951 stream, <= 64 KiB out), two alternating phases per round of <= 256
-//   symbols: lane 0 decodes Huffman symbols into a shared-memory token queue, then all 32 lanes materialise the queue
-//   (warp scan of token lengths -> output positions; all literals of a 32-token chunk in one store; matches replayed
-//   in order, each copied by the whole warp).  Throughput comes from block-level parallelism (28 warps per SM).
+// k_inflate_q2: one warp per TWO BGZF blocks (RFC 1951 streams, <= 64 KiB out each), two alternating phases per round
+//   of <= 128 symbols: lanes 0 and 16 decode Huffman symbols of their streams into shared-memory token queues, then
+//   all 32 lanes materialise one queue after the other (warp scan of token lengths -> output positions; all literals
+//   of a 32-token chunk in one store; independent short matches replayed concurrently, one lane each).
 // k_crc32: one thread per block, slicing-by-4.
 // k_walk<>: one thread per index entry point (BAI linear-index offsets and chunk bounds are record-aligned); each
 //   walks block_size -> next record until the next entry point; a scan of the counts in between gives every walker
@@ -26,10 +26,14 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_inflate_q2: the production inflate kernel.  Same two-phase structure as k_inflate_q, on the lean decode core of
-// inflate_core.cuh (32-bit look-ahead bit reader, one table lookup per code with base/extra-bits packed in the
-// entry, sticky error flag instead of divergent breaks) and a cheaper materialisation step (one predicated
-// load/store per <= 32-byte match; overlapping matches use the period trick instead of a modulo per byte).
+// k_inflate_q2: the production inflate kernel.  Two-phase rounds on the lean decode core of inflate_core.cuh (32-bit
+// look-ahead bit reader, one table lookup per code, one 64-bit look-ahead per match, sticky error flag instead of
+// divergent breaks) and a materialisation step with one predicated load/store per <= 32-byte match.
+//
+// TWO streams per warp: lanes 0 and 16 each decode their own BGZF block in the same instructions (phase 1 is a
+// serial dependency chain per stream - 72 % of the kernel's issue slots with one active lane - so a second chain in
+// the same warp is almost free); phase 2 then replays the two queues one after the other with all 32 lanes.
+// 16-bit table entries keep a stream at 3.7 KB of shared memory, so 28 warps = 56 streams are resident per SM.
 // The decode core is unit-tested on the host (tests/host_inflate_harness.cpp) against zlib's CRC32.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kQ2Warps = 4;
@@ -46,12 +50,12 @@ struct SmemAccess {
     uint32_t lit_a, dist_a, q_a;
     __device__ __forceinline__ uint32_t lit(uint32_t byte_off) const {
         uint32_t r;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(lit_a + byte_off) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + byte_off) : "memory");
         return r;
     }
     __device__ __forceinline__ uint32_t dist(uint32_t byte_off) const {
         uint32_t r;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(dist_a + byte_off) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(dist_a + byte_off) : "memory");
         return r;
     }
     __device__ __forceinline__ void put(uint32_t byte_off, uint32_t v) const {
@@ -63,6 +67,18 @@ struct SmemAccess {
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + 2u * len) : "memory");
         return r;
     }
+    template <bool DIST> __device__ __forceinline__ uint32_t first() const {
+        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_first) : offsetof(inflate_core::Tables, lit_first);
+        uint32_t r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off) : "memory");
+        return r;
+    }
+    template <bool DIST> __device__ __forceinline__ uint32_t index() const {
+        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_index) : offsetof(inflate_core::Tables, lit_index);
+        uint32_t r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off) : "memory");
+        return r;
+    }
     template <bool DIST> __device__ __forceinline__ uint32_t sorted(uint32_t i) const {
         constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_sorted) : offsetof(inflate_core::Tables, lit_sorted);
         uint32_t r;
@@ -71,37 +87,124 @@ struct SmemAccess {
     }
 };
 
+// Phase 2: all 32 lanes materialise one stream's token queue q[0..nq) behind out[pos_base); returns the new pos_base.
+__device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int nq, uint8_t* out, uint32_t pos_base, int lane) {
+    using namespace inflate_core;
+    for (int base = 0; base < nq; base += 32) {
+        const bool valid = base + lane < nq;
+        const uint32_t t = valid ? q[base + lane] : 0u;
+        const bool is_match = (t >> 31) != 0;
+        const bool is_skip = !is_match && (t & kTokSkip);
+        const uint32_t len = is_match ? (t & 0x1ffu) : (is_skip ? (t & 0xffffffu) : (valid ? 1u : 0u));
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t pos = pos_base + incl - len;
+        if (valid && !is_match && !is_skip) out[pos] = uint8_t(t);
+        // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
+        // first pending token reads only finished output, so all of them are copied at once, each by its own lane
+        // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
+        // they reach the front.
+        uint32_t pending = __ballot_sync(FULL, is_match);
+        const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
+        const bool is_long = is_match && own_len > 32u;
+        const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
+        __syncwarp();
+        while (pending) {
+            const int first = __ffs(pending) - 1;
+            const uint32_t front = __shfl_sync(FULL, pos, first);
+            if (__shfl_sync(FULL, uint32_t(is_long), first)) {
+                const uint32_t mt = __shfl_sync(FULL, t, first);
+                const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
+                uint8_t* dst = out + front;
+                {   // the first 32 bytes never depend on bytes written in this step
+                    const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
+                    dst[lane] = dst[so];
+                }
+                // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
+                const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
+                for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
+                    __syncwarp();
+                    if (j < mlen) dst[j] = dst[int(j) - int(K)];
+                }
+                pending &= ~(1u << first);
+                __syncwarp();
+                continue;
+            }
+            const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
+            if (ready) {
+                for (uint32_t done = 0; done < own_len; done += 8u) {
+                    const uint32_t n = min(own_len - done, 8u);
+                    uint8_t* d = out + pos + done;
+                    if (pos + done >= 8u) {
+                        // eight source bytes from three aligned words + two funnel shifts (raw is cudaMalloc'ed; the
+                        // bytes around [sp, sp + 8) that the words also cover are finished output or slack)
+                        const uint8_t* sp = d - max(own_dist, 8u);
+                        const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+                        const uint32_t sh = uint32_t(sa & 3u) * 8u;
+                        const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2];
+                        const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                        uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
+                        if (own_dist < 8u) {
+                            uint64_t rep = w >> (8u * (8u - own_dist));
+                            for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
+                            w = rep;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
+                    } else {
+                        for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
+                    }
+                }
+            }
+            pending &= ~__ballot_sync(FULL, ready);
+            __syncwarp();
+        }
+        pos_base += __shfl_sync(FULL, incl, 31);
+    }
+    return pos_base;
+}
+
+template <int kStreams>
 __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
                                                                   const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
-    __shared__ Q2Smem s_mem[kQ2Warps];
+    static_assert(kStreams == 1 || kStreams == 2, "one or two streams per warp");
+    __shared__ Q2Smem s_mem[kQ2Warps][kStreams];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kQ2Warps + wid;
-    if (b >= n_blocks) return;
-    Tables& T = s_mem[wid].T;
-    volatile uint32_t* q = s_mem[wid].q;
-    SmemAccess acc{uint32_t(__cvta_generic_to_shared(s_mem[wid].T.lit)), uint32_t(__cvta_generic_to_shared(s_mem[wid].T.dist)),
-                   uint32_t(__cvta_generic_to_shared(s_mem[wid].q))};
+    const int sub = kStreams == 2 ? lane >> 4 : 0;          // the stream this lane belongs to in phase 1
+    const bool dec = kStreams == 2 ? (lane & 15) == 0 : lane == 0;      // lanes 0 (and 16) decode
+    const int b = (blockIdx.x * kQ2Warps + wid) * kStreams + sub;
+    if ((blockIdx.x * kQ2Warps + wid) * kStreams >= n_blocks) return;       // whole warp idle
+    Tables& T = s_mem[wid][sub].T;
+    volatile uint32_t* q = s_mem[wid][sub].q;
+    SmemAccess acc{uint32_t(__cvta_generic_to_shared(s_mem[wid][sub].T.lit)), 0u, 0u};
     // identity shuffle: ptxas cannot re-derive the value from %tid inside the decode loop (it otherwise rebuilds the
     // address with six instructions per token); dist and q are fixed offsets from it
     acc.lit_a = __shfl_sync(FULL, acc.lit_a, lane);
-    acc.dist_a = acc.lit_a + uint32_t(sizeof(uint32_t) << kLitBits);
-    acc.q_a = acc.lit_a + uint32_t(sizeof(inflate_core::Tables));
-    const InflateBlock blk = blocks[b];
+    acc.dist_a = acc.lit_a + uint32_t(sizeof(uint16_t) << kLitBits);
+    acc.q_a = acc.lit_a + uint32_t(sizeof(Tables));
+    bool fin = b >= n_blocks;                               // this lane's stream is finished (or absent)
+    InflateBlock blk{0u, 0u, 0u, 0u};
+    if (!fin) blk = blocks[b];
     uint8_t* out = raw + blk.out_off;
     const uint32_t out_len = blk.out_len;
-    inflate_core::BitReader br;
+    BitReader br;
     br.base = reinterpret_cast<const uint32_t*>(comp);     // cudaMalloc'ed: aligned
     br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
-    if (lane == 0) br.init(br.base, blk.in_off);
+    if (dec && !fin) br.init(br.base, blk.in_off);
     const uint64_t end_bit = (uint64_t(blk.in_off) + blk.in_len) * 8u;
     uint32_t op_dec = 0, pos_base = 0;
     int phase = 0, last = 0;
     for (;;) {
-        int nq = 0, state = 0;       // state: 0 = go on, 1 = stream finished, 2 = error
-        if (lane == 0) {
+        int nq = 0, state = fin ? 3 : 0;       // state: 0 = go on, 1 = stream finished, 2 = error, 3 = nothing to do
+        if (dec && !fin) {
             if (phase == 0) {
-                const int h = read_block_header(br, T, &last);
+                const int h = read_block_header(br, T, reinterpret_cast<uint8_t*>(const_cast<uint32_t*>(q)), &last);
                 if (h == 2) state = 2;
                 else if (h == 1) {
                     br.consume((32u - br.bo) & 7u);
@@ -128,88 +231,26 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
                 if (bad || op_dec > out_len || br.bit_pos() > end_bit) state = 2;
             }
         }
-        nq = __shfl_sync(FULL, nq, 0);
-        state = __shfl_sync(FULL, state, 0);
-        if (state == 2) break;
         __syncwarp();
-        // ---- phase 2: materialise the queue -----------------------------------------------------------------------------------
-        for (int base = 0; base < nq; base += 32) {
-            const bool valid = base + lane < nq;
-            const uint32_t t = valid ? q[base + lane] : 0u;
-            const bool is_match = (t >> 31) != 0;
-            const bool is_skip = !is_match && (t & kTokSkip);
-            const uint32_t len = is_match ? (t & 0x1ffu) : (is_skip ? (t & 0xffffffu) : (valid ? 1u : 0u));
-            uint32_t incl = len;
+        // ---- phase 2: materialise the two queues, one after the other, with the whole warp ------------------------------
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const uint32_t pos = pos_base + incl - len;
-            if (valid && !is_match && !is_skip) out[pos] = uint8_t(t);
-            // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
-            // first pending token reads only finished output, so all of them are copied at once, each by its own lane
-            // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
-            // they reach the front.
-            uint32_t pending = __ballot_sync(FULL, is_match);
-            const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
-            const bool is_long = is_match && own_len > 32u;
-            const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
-            __syncwarp();
-            while (pending) {
-                const int first = __ffs(pending) - 1;
-                const uint32_t front = __shfl_sync(FULL, pos, first);
-                if (__shfl_sync(FULL, uint32_t(is_long), first)) {
-                    const uint32_t mt = __shfl_sync(FULL, t, first);
-                    const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
-                    uint8_t* dst = out + front;
-                    {   // the first 32 bytes never depend on bytes written in this step
-                        const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
-                        dst[lane] = dst[so];
-                    }
-                    // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
-                    const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
-                    for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
-                        __syncwarp();
-                        if (j < mlen) dst[j] = dst[int(j) - int(K)];
-                    }
-                    pending &= ~(1u << first);
-                    __syncwarp();
-                    continue;
-                }
-                const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
-                if (ready) {
-                    for (uint32_t done = 0; done < own_len; done += 8u) {
-                        const uint32_t n = min(own_len - done, 8u);
-                        uint8_t* d = out + pos + done;
-                        if (pos + done >= 8u) {
-                            const uint8_t* sp = d - max(own_dist, 8u);
-                            uint32_t lo = 0, hi = 0;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { lo |= uint32_t(sp[k]) << (8 * k); hi |= uint32_t(sp[4 + k]) << (8 * k); }
-                            uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
-                            if (own_dist < 8u) {
-                                uint64_t rep = w >> (8u * (8u - own_dist));
-                                for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
-                                w = rep;
-                            }
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
-                        } else {
-                            for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
-                        }
-                    }
-                }
-                pending &= ~__ballot_sync(FULL, ready);
-                __syncwarp();
-            }
-            pos_base += __shfl_sync(FULL, incl, 31);
+        for (int s = 0; s < kStreams; ++s) {
+            const int src = 16 * s;
+            const int st_s = __shfl_sync(FULL, state, src);
+            const int nq_s = __shfl_sync(FULL, nq, src);
+            const uint32_t pb_s = __shfl_sync(FULL, pos_base, src);
+            const uint32_t oo_s = __shfl_sync(FULL, blk.out_off, src);
+            if (st_s >= 2 || nq_s == 0) continue;            // warp-uniform
+            const uint32_t pb_new = materialise(s_mem[wid][s].q, nq_s, raw + oo_s, pb_s, lane);
+            if (lane == src) pos_base = pb_new;
         }
         __syncwarp();
-        if (state == 1) break;
+        if (dec && !fin && state != 0) {
+            if (state == 2 || op_dec != out_len || pos_base != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
+            fin = true;
+        }
+        if (__all_sync(FULL, fin || !dec)) break;
     }
-    const uint32_t final_dec = __shfl_sync(FULL, op_dec, 0);
-    if (lane == 0 && (final_dec != out_len || pos_base != out_len)) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -317,8 +358,12 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s) {
     if (n_blocks <= 0) return;
-    const int grid = (n_blocks + kQ2Warps - 1) / kQ2Warps;
-    k_inflate_q2<<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    // BSG_INFLATE_STREAMS=1 selects the one-stream-per-warp instantiation (kept for A/B measurements)
+    const int streams = (getenv("BSG_INFLATE_STREAMS") && atoi(getenv("BSG_INFLATE_STREAMS")) == 1) ? 1 : 2;
+    const int per_cta = kQ2Warps * streams;
+    const int grid = (n_blocks + per_cta - 1) / per_cta;
+    if (streams == 1) k_inflate_q2<1><<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    else k_inflate_q2<2><<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
 }
 
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,

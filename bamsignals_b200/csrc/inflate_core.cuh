@@ -1,6 +1,9 @@
 // Single-lane DEFLATE decode core shared by the GPU inflate kernel and its host-side unit harness
 // (tests/host_inflate_harness.cpp compiles this header with a plain C++ compiler).  Everything here is executed by ONE
 // thread per BGZF block: bit reader, decode-table construction, and "phase 1" = Huffman symbols -> token queue.
+//
+// Shared-memory budget: 3776 bytes per stream (16-bit table entries, 128-token queue that doubles as the code-length
+// scratch while a block header is parsed), so that two streams per warp still leave 28 warps resident per SM.
 #pragma once
 #include <cstdint>
 
@@ -17,15 +20,23 @@ namespace inflate_core {
 #define BSG_LIT_BITS 10
 #endif
 constexpr int kLitBits = BSG_LIT_BITS, kDistBits = 8;
-constexpr int kQueue = 256;
+constexpr int kQueue = 128;
 
 // token: literal = byte ; match = 1 << 31 | (dist - 1) << 16 | len ; skip (stored bytes already in place) = 1 << 30 | len
 constexpr uint32_t kTokMatch = 0x80000000u, kTokSkip = 0x40000000u;
 
-// decode-table entry: [3:0] code length, [7:4] extra-bit count, [9:8] type, [31:16] literal byte / length base /
-// distance base.  Slots no code of <= kLitBits (kDistBits) bits maps to hold kTypeBad with length 0: one type test
-// sends literals and lengths down their fast paths and everything rare (end of block, long codes, errors) elsewhere.
-enum : uint32_t { kTypeLit = 0u << 8, kTypeLen = 1u << 8, kTypeEob = 2u << 8, kTypeBad = 3u << 8, kTypeMask = 3u << 8 };
+// 16-bit decode-table entries.
+//   literal/length code:  [3:0] code length, [4] 0 = literal / 1 = anything else,
+//                         literal: [15:8] the byte;  otherwise [7:5] class: 0..5 = length symbol with that many extra
+//                         bits and [15:8] = base length - 3;  7 = end of block;  6 = not decodable from this entry
+//                         (code length 0: the code is longer than the primary table -> canonical slow path;
+//                          code length > 0: invalid symbol 286/287)
+//   distance code:        [3:0] code length (0 = slow path), [7:4] extra bits, [9:8] mantissa m: base = (m << extra) + 1,
+//                         [10] invalid symbol (30/31)
+// One test of bit 4 separates literals from everything else; one test of the class separates lengths from the rare rest.
+constexpr uint32_t kNonLit = 0x10u, kClsShift = 5, kClsEob = 7u, kClsOther = 6u;
+constexpr uint32_t kLitUnset = kNonLit | (kClsOther << kClsShift);      // length 0: take the slow path
+constexpr uint32_t kDistBad = 0x400u;
 
 BSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
@@ -77,55 +88,92 @@ struct BitReader {
 };
 
 struct Tables {
-    uint32_t lit[1 << kLitBits];
-    uint32_t dist[1 << kDistBits];
+    uint16_t lit[1 << kLitBits];
+    uint16_t dist[1 << kDistBits];
     uint16_t lit_sorted[288];
     uint16_t dist_sorted[32];
     uint16_t lit_count[16], dist_count[16];
-    uint8_t lens[320];
+    // canonical-decode state after the code lengths the primary tables cover (see slow_entry)
+    uint16_t lit_first, lit_index, dist_first, dist_index;
 };
+constexpr int kLensBytes = 320;     // code lengths of one block header: 288 literal/length + 32 distance symbols
+static_assert(kQueue * 4 >= kLensBytes, "the token queue doubles as the code-length scratch");
 
 BSG_HD uint32_t lit_entry(int sym, int len) {
-    if (sym < 256) return uint32_t(len) | kTypeLit | (uint32_t(sym) << 16);
-    if (sym == 256) return uint32_t(len) | kTypeEob;
-    if (sym > 285) return uint32_t(len) | kTypeBad;
+    if (sym < 256) return uint32_t(len) | (uint32_t(sym) << 8);
+    if (sym == 256) return uint32_t(len) | kNonLit | (kClsEob << kClsShift);
+    if (sym > 285) return uint32_t(len) | kNonLit | (kClsOther << kClsShift);
     uint32_t eb, base;
     if (sym < 265) { eb = 0; base = uint32_t(sym - 254); }
     else if (sym == 285) { eb = 0; base = 258; }
     else { eb = uint32_t(sym - 261) >> 2; base = ((4u + (uint32_t(sym - 265) & 3u)) << eb) + 3u; }
-    return uint32_t(len) | (eb << 4) | kTypeLen | (base << 16);
+    return uint32_t(len) | kNonLit | (eb << kClsShift) | ((base - 3u) << 8);
 }
 BSG_HD uint32_t dist_entry(int sym, int len) {
-    if (sym > 29) return uint32_t(len) | kTypeBad;
-    uint32_t eb, base;
-    if (sym < 4) { eb = 0; base = uint32_t(sym + 1); }
-    else { eb = (uint32_t(sym) >> 1) - 1u; base = ((2u + (uint32_t(sym) & 1u)) << eb) + 1u; }
-    return uint32_t(len) | (eb << 4) | (base << 16);
+    if (sym > 29) return uint32_t(len) | kDistBad;
+    uint32_t eb, mant;
+    if (sym < 4) { eb = 0; mant = uint32_t(sym); }
+    else { eb = (uint32_t(sym) >> 1) - 1u; mant = 2u + (uint32_t(sym) & 1u); }
+    return uint32_t(len) | (eb << 4) | (mant << 8);
 }
 
-// canonical decode of a code longer than the primary table (RFC 1951 3.2.2) from the 32 peeked bits;
-// returns the symbol and its code length, or -1.  DIST selects the distance code's count / sorted arrays.
+// Table / queue access of fill_queue.  The host harness (and any generic caller) uses plain arrays; the kernel
+// passes shared-memory byte addresses and ld.shared / st.shared so that the addresses stay in registers.
+struct ArrayAccess {
+    const Tables* T;
+    uint32_t* q;
+    BSG_HD uint32_t lit(uint32_t byte_off) const { return T->lit[byte_off >> 1]; }
+    BSG_HD uint32_t dist(uint32_t byte_off) const { return T->dist[byte_off >> 1]; }
+    BSG_HD void put(uint32_t byte_off, uint32_t v) const { q[byte_off >> 2] = v; }
+    template <bool DIST> BSG_HD uint32_t count(uint32_t len) const { return DIST ? T->dist_count[len] : T->lit_count[len]; }
+    template <bool DIST> BSG_HD uint32_t sorted(uint32_t i) const { return DIST ? T->dist_sorted[i] : T->lit_sorted[i]; }
+    template <bool DIST> BSG_HD uint32_t first() const { return DIST ? T->dist_first : T->lit_first; }
+    template <bool DIST> BSG_HD uint32_t index() const { return DIST ? T->dist_index : T->lit_index; }
+};
+
+// Canonical decode of a code longer than the primary table (RFC 1951 3.2.2) from the 32 peeked bits: returns the
+// table entry the symbol would have had (with its real code length), or an "invalid" entry.  The primary lookup has
+// already ruled out every code of up to kLitBits (kDistBits) bits, so the search starts behind them: the (first,
+// index) pair of the canonical walk at that point depends only on the code-length counts and is stored with the
+// tables; most long codes are one or two bits longer than the table, so the loop runs once or twice.
+// Deliberately NOT inlined into the hot loop on the device: about one token in twenty comes here, and the loop body
+// must stay small for the instruction cache (measured: 4 % of the kernel's stall samples were instruction fetches).
 template <bool DIST, class A>
-BSG_HD int slow_symbol(uint32_t v, const A& acc, int* len_out) {
-    int code = 0, first = 0, index = 0;
-    for (int len = 1; len <= 15; ++len) {
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+uint32_t slow_entry(uint32_t v, const A& acc) {
+    constexpr int kBits = DIST ? kDistBits : kLitBits;
+    int code = int(rev_bits(v & ((1u << kBits) - 1u), kBits)) << 1;       // the first kBits bits, MSB first
+    int first = int(acc.template first<DIST>()), index = int(acc.template index<DIST>());
+    v >>= kBits;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int len = kBits + 1; len <= 15; ++len) {
         code |= int(v & 1u);
         v >>= 1;
         const int c = int(acc.template count<DIST>(uint32_t(len)));
-        if (code - c < first) { *len_out = len; return int(acc.template sorted<DIST>(uint32_t(index + (code - first)))); }
+        if (code - c < first) {
+            const int sym = int(acc.template sorted<DIST>(uint32_t(index + (code - first))));
+            return DIST ? dist_entry(sym, len) : lit_entry(sym, len);
+        }
         index += c;
         first += c;
         first <<= 1;
         code <<= 1;
     }
-    *len_out = 15;
-    return -1;
+    return DIST ? (15u | kDistBad) : (15u | kNonLit | (kClsOther << kClsShift));
 }
 
 // Serial table construction by the owning thread.  is_dist selects the entry format.  Returns false when the code
 // is over-subscribed.
-BSG_HD bool build_table(const uint8_t* lens, int n, uint32_t* primary, int bits, uint16_t* count, uint16_t* sorted, bool is_dist) {
-    for (int i = 0; i < (1 << bits); ++i) primary[i] = kTypeBad;   // length 0 + kTypeBad = "not in the primary table"
+BSG_HD bool build_table(const uint8_t* lens, int n, uint16_t* primary, int bits, uint16_t* count, uint16_t* sorted, bool is_dist,
+                        uint16_t* first_out, uint16_t* index_out) {
+    const uint16_t unset = is_dist ? uint16_t(0) : uint16_t(kLitUnset);      // code length 0 = not in the primary table
+    for (int i = 0; i < (1 << bits); ++i) primary[i] = unset;
     int cnt[16];
     for (int l = 0; l < 16; ++l) cnt[l] = 0;
     for (int s = 0; s < n; ++s) cnt[lens[s] & 15]++;
@@ -136,13 +184,18 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint32_t* primary, int bits,
     next[0] = 0; offs[0] = 0; next[1] = 0; offs[1] = 0;
     for (int l = 1; l < 15; ++l) { next[l + 1] = (next[l] + cnt[l]) << 1; offs[l + 1] = offs[l] + cnt[l]; }
     for (int l = 0; l < 16; ++l) count[l] = uint16_t(cnt[l]);
+    {   // state of the canonical walk after lengths 1..bits (an over-subscribed code may overflow 16 bits: flagged by ok)
+        int first = 0, index = 0;
+        for (int l = 1; l <= bits; ++l) { index += cnt[l]; first += cnt[l]; first <<= 1; }
+        *first_out = uint16_t(first); *index_out = uint16_t(index);
+    }
     for (int s = 0; s < n; ++s) {
         const int l = lens[s] & 15;
         if (!l) continue;
         const uint32_t code = uint32_t(next[l]++);
         sorted[offs[l]++] = uint16_t(s);
         if (l <= bits) {
-            const uint32_t e = is_dist ? dist_entry(s, l) : lit_entry(s, l);
+            const uint16_t e = uint16_t(is_dist ? dist_entry(s, l) : lit_entry(s, l));
             for (int k = int(rev_bits(code, uint32_t(l))); k < (1 << bits); k += (1 << l)) primary[k] = e;
         }
     }
@@ -150,8 +203,9 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint32_t* primary, int bits,
 }
 
 // Block header: reads BFINAL/BTYPE and, for Huffman blocks, the code lengths, then builds the tables.
+// `lens` is kLensBytes of scratch (the kernel lends the empty token queue).
 // Returns 0 = Huffman block ready, 1 = stored block (caller handles LEN/NLEN), 2 = error.
-BSG_HD int read_block_header(BitReader& br, Tables& T, int* last) {
+BSG_HD int read_block_header(BitReader& br, Tables& T, uint8_t* lens, int* last) {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     uint32_t v = br.peek();
     *last = int(v & 1u);
@@ -161,8 +215,8 @@ BSG_HD int read_block_header(BitReader& br, Tables& T, int* last) {
     if (btype == 3) return 2;
     int nlit = 288, ndist = 32;
     if (btype == 1) {
-        for (int s = 0; s < 288; ++s) T.lens[s] = uint8_t(s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8)));
-        for (int s = 0; s < 32; ++s) T.lens[288 + s] = 5;
+        for (int s = 0; s < 288; ++s) lens[s] = uint8_t(s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8)));
+        for (int s = 0; s < 32; ++s) lens[288 + s] = 5;
     } else {
         uint8_t* cl = reinterpret_cast<uint8_t*>(T.lit);      // code-length table borrows the (not yet built) lit table
         v = br.peek();
@@ -193,36 +247,24 @@ BSG_HD int read_block_header(BitReader& br, Tables& T, int* last) {
             const uint32_t e = cl[v & 127u];
             const int l = int(e >> 5), s = int(e & 31u);
             if (!l) return 2;
-            if (s < 16) { T.lens[i++] = uint8_t(s); br.consume(uint32_t(l)); continue; }
+            if (s < 16) { lens[i++] = uint8_t(s); br.consume(uint32_t(l)); continue; }
             int rep, val = 0;
             uint32_t used = uint32_t(l);
-            if (s == 16) { if (i == 0) return 2; val = T.lens[i - 1]; rep = 3 + int((v >> l) & 3u); used += 2; }
+            if (s == 16) { if (i == 0) return 2; val = lens[i - 1]; rep = 3 + int((v >> l) & 3u); used += 2; }
             else if (s == 17) { rep = 3 + int((v >> l) & 7u); used += 3; }
             else { rep = 11 + int((v >> l) & 127u); used += 7; }
             br.consume(used);
             if (i + rep > total) return 2;
-            while (rep--) T.lens[i++] = uint8_t(val);
+            while (rep--) lens[i++] = uint8_t(val);
         }
-        if (T.lens[256] == 0) return 2;
-        for (int k = ndist - 1; k >= 0; --k) T.lens[288 + k] = T.lens[nlit + k];
-        for (int k = nlit; k < 288; ++k) T.lens[k] = 0;
+        if (lens[256] == 0) return 2;
+        for (int k = ndist - 1; k >= 0; --k) lens[288 + k] = lens[nlit + k];
+        for (int k = nlit; k < 288; ++k) lens[k] = 0;
     }
-    bool ok = build_table(T.lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, false);
-    ok = build_table(T.lens + 288, ndist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true) && ok;
+    bool ok = build_table(lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, false, &T.lit_first, &T.lit_index);
+    ok = build_table(lens + 288, ndist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true, &T.dist_first, &T.dist_index) && ok;
     return ok ? 0 : 2;
 }
-
-// Table / queue access of fill_queue.  The host harness (and any generic caller) uses plain arrays; the kernel
-// passes shared-memory byte addresses and ld.shared / st.shared so that the addresses stay in registers.
-struct ArrayAccess {
-    const Tables* T;
-    uint32_t* q;
-    BSG_HD uint32_t lit(uint32_t byte_off) const { return T->lit[byte_off >> 2]; }
-    BSG_HD uint32_t dist(uint32_t byte_off) const { return T->dist[byte_off >> 2]; }
-    BSG_HD void put(uint32_t byte_off, uint32_t v) const { q[byte_off >> 2] = v; }
-    template <bool DIST> BSG_HD uint32_t count(uint32_t len) const { return DIST ? T->dist_count[len] : T->lit_count[len]; }
-    template <bool DIST> BSG_HD uint32_t sorted(uint32_t i) const { return DIST ? T->dist_sorted[i] : T->lit_sorted[i]; }
-};
 
 // Phase 1: decode symbols into the queue until it holds kQueue tokens or the block ends.
 // *op_dec = bytes decoded so far (updated).  Returns the number of tokens; *eob is set at end-of-block; *bad is
@@ -231,53 +273,47 @@ struct ArrayAccess {
 // <= 28 bits) and consumed once.
 template <class A>
 BSG_HD int fill_queue(BitReader& br, const A& acc, uint32_t* op_dec, int* eob, int* bad) {
-    constexpr uint32_t kLitMask4 = ((1u << kLitBits) - 1u) << 2, kDistMask4 = ((1u << kDistBits) - 1u) << 2;
+    constexpr uint32_t kLitMask2 = ((1u << kLitBits) - 1u) << 1, kDistMask2 = ((1u << kDistBits) - 1u) << 1;
     uint32_t qo = 0;                  // byte offset of the next queue slot
     uint32_t op = *op_dec;
     int err = 0;
     *eob = 0;
     do {
         const uint32_t v = br.peek();
-        uint32_t e = acc.lit((v << 2) & kLitMask4);
-        uint32_t type = e & kTypeMask;
-        if (type == kTypeLit) {                       // literal with a short code: the common non-match case
-            acc.put(qo, e >> 16);
+        uint32_t e = acc.lit((v << 1) & kLitMask2);
+        if (!(e & kNonLit)) {                         // literal with a short code: the common non-match case
+            acc.put(qo, e >> 8);
             br.consume_short(e & 15u);
             qo += 4; ++op;
             continue;
         }
-        if (type != kTypeLen) {                       // rare: end of block, a code longer than the primary table, garbage
+        uint32_t cls = (e >> kClsShift) & 7u;
+        if (cls >= kClsOther) {                       // rare: end of block, a code longer than the primary table, garbage
             if (!(e & 15u)) {
-                int l;
-                const int sym = slow_symbol<false>(v, acc, &l);
-                e = sym < 0 ? (uint32_t(l) | kTypeBad) : lit_entry(sym, l);
-                type = e & kTypeMask;
+                e = slow_entry<false>(v, acc);
+                cls = (e >> kClsShift) & 7u;
+                if (!(e & kNonLit)) {
+                    acc.put(qo, e >> 8);
+                    br.consume_short(e & 15u);
+                    qo += 4; ++op;
+                    continue;
+                }
             }
-            if (type == kTypeLit) {
-                acc.put(qo, e >> 16);
+            if (cls >= kClsOther) {
                 br.consume_short(e & 15u);
-                qo += 4; ++op;
-                continue;
-            }
-            if (type != kTypeLen) {
-                br.consume_short(e & 15u);
-                if (type == kTypeEob) *eob = 1; else err = 1;
+                if (cls == kClsEob) *eob = 1; else err = 1;
                 break;
             }
         }
-        const uint32_t len = e & 15u, eb = (e >> 4) & 15u, used = len + eb;
-        const uint32_t mlen = (e >> 16) + ((v >> len) & ~(~0u << eb));
+        const uint32_t len = e & 15u, used = len + cls;            // cls = number of extra bits
+        const uint32_t mlen = (e >> 8) + 3u + ((v >> len) & ~(~0u << cls));
         const uint32_t v2 = funnel_r(v, br.peek_hi(), used);      // used <= 20
-        uint32_t d = acc.dist((v2 << 2) & kDistMask4);
-        if (!(d & 15u)) {
-            int l;
-            const int sym = slow_symbol<true>(v2, acc, &l);
-            d = sym < 0 ? (uint32_t(l) | kTypeBad) : dist_entry(sym, l);
-        }
+        uint32_t d = acc.dist((v2 << 1) & kDistMask2);
+        if (!(d & 15u)) d = slow_entry<true>(v2, acc);
         const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
-        uint32_t mdist = (d >> 16) + ((v2 >> dl) & ~(~0u << deb));
+        uint32_t mdist = (((d >> 8) & 3u) << deb) + 1u + ((v2 >> dl) & ~(~0u << deb));
         br.consume(used + dl + deb);                               // <= 48
-        if ((d & kTypeMask) != 0u || mdist > op) { err = 1; mdist = 1; }
+        if ((d & kDistBad) != 0u || mdist > op) { err = 1; mdist = 1; }
         acc.put(qo, kTokMatch | ((mdist - 1u) << 16) | mlen);
         qo += 4; op += mlen;
     } while (qo < uint32_t(kQueue) * 4u);
@@ -288,4 +324,3 @@ BSG_HD int fill_queue(BitReader& br, const A& acc, uint32_t* op_dec, int* eob, i
 
 }  // namespace inflate_core
 }  // namespace bsg
-

@@ -23,7 +23,7 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
     for (;;) {
         int nq = 0, done = 0;
         if (phase == 0) {
-            const int h = read_block_header(br, T, &last);
+            const int h = read_block_header(br, T, reinterpret_cast<uint8_t*>(q), &last);
             if (h == 2) return 2;
             if (h == 1) {
                 br.consume((32 - br.bo) & 7);

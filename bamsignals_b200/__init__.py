@@ -4,6 +4,7 @@ Only what the hot path needs lives here: csrc/ (CUDA kernels, host fetch pipelin
 and api.py (the Python mirror of the R functions bamCount / bamProfile / bamCoverage and of CountSignals).
 """
 from .api import (BamsignalsError, CountSignals, GRanges, Stage, bamCount, bamCoverage, bamProfile,  # noqa: F401
-                  core_args, coverage_core, default_opts, flagMask, lib, pileup_core, timings)
+                  core_args, coverage_core, default_opts, flagMask, lib, pileup_core, timings,
+                  writeSamAsBamAndIndex)
 
 __version__ = "0.1.0"

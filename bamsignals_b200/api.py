@@ -270,6 +270,8 @@ def lib():
     L.bsg_coverage_staged.restype = C.c_int
     L.bsg_stage_close.argtypes = [C.c_void_p]
     L.bsg_stage_close.restype = None
+    L.bsg_write_sam_as_bam_and_index.argtypes = [C.c_char_p, C.c_char_p]
+    L.bsg_write_sam_as_bam_and_index.restype = C.c_int
     _lib = L
     return L
 
@@ -291,6 +293,13 @@ def default_opts(**kw) -> BsgOpts:
         else:
             setattr(o, k, v)
     return o
+
+
+def writeSamAsBamAndIndex(sampath, bampath) -> bool:
+    """bamsignals:::writeSamAsBamAndIndex (R/RcppExports.R:20-22, src/bamsignals.cpp:496-534): SAM text ->
+    coordinate-sorted BAM + .bai.  Host-only."""
+    _check(lib().bsg_write_sam_as_bam_and_index(os.fsencode(os.path.expanduser(sampath)), os.fsencode(os.path.expanduser(bampath))))
+    return True
 
 
 def timings() -> dict:

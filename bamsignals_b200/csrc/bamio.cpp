@@ -53,6 +53,8 @@ BamFile::BamFile(const std::string& path) : path_(path) {
     if (p == MAP_FAILED) { ::close(fd_); fd_ = -1; fail(BSG_EOPEN, "Fail to open BAM file " + path); }
     data_ = static_cast<const uint8_t*>(p);
     try {
+        // the reference would read CRAM through htslib (given a reference genome); this library reads BAM only
+        if (size_ >= 4 && memcmp(data_, "CRAM", 4) == 0) fail(BSG_EFORMAT, "CRAM input is not supported (convert it to BAM): " + path);
         parse_header();
         load_index();
     } catch (...) {

@@ -25,6 +25,7 @@
 #include "pool.h"
 
 namespace bsg {
+void write_sam_as_bam_and_index(const char* sampath, const char* bampath);      // bamwrite.cpp
 namespace {
 
 thread_local std::string g_err;
@@ -1390,6 +1391,15 @@ void bsg_shutdown(void) {
     for (auto& c : g_ctx) c.release();
     g_pool.reset();
     g_bams.clear();
+}
+
+int bsg_write_sam_as_bam_and_index(const char* sampath, const char* bampath) {
+    return guarded([&] {
+        // a cached handle of a file this call replaces must not survive it
+        const std::string p = bampath ? bampath : "";
+        for (auto it = g_bams.begin(); it != g_bams.end();) it = (*it)->path() == p ? g_bams.erase(it) : it + 1;
+        write_sam_as_bam_and_index(sampath, bampath);
+    });
 }
 
 const char* bsg_version(void) { return "bamsignals_cuda 0.1.0 (sm_100a)"; }

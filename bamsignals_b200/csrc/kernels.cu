@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
     __shared__ int s_kept, s_arrived, s_ghlo, s_ghhi;
     // which batch does this chunk belong to?
     DecodeBatch B = single;
+    int bi = 0;
     if (table) {
         int lo = 0, hi = n_batches - 1;
         while (lo < hi) {
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
             if (int(blockIdx.x) >= table[mid].chunk0) lo = mid; else hi = mid - 1;
         }
         B = table[lo];
+        bi = lo;
     }
     const int i0 = (int(blockIdx.x) - B.chunk0) * kThreads;
     const int i = i0 + threadIdx.x;
@@ -205,7 +207,16 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
             else { w0 = gld(b); w1 = gld(b + 4); w2 = gld(b + 8); }
             ptid = __funnelshift_r(w0, w1, sh);
             ppos = int32_t(__funnelshift_r(w1, w2, sh));
-        } else if (B.row0 > 0) {
+        } else if (table && bi > 0) {
+            // first record of a resident batch: the record before it is the last one of the batch before, which this
+            // same launch decodes (its table row may not be written yet): read it from the raw bytes
+            const DecodeBatch Bp = table[bi - 1];
+            const GlobalLd pld{Bp.raw};
+            const uint32_t a = __ldg(Bp.offs + Bp.n - 1) + 4, b = a & ~3u, sh = (a & 3u) * 8;
+            const uint32_t w0 = pld(b), w1 = pld(b + 4), w2 = pld(b + 8);
+            ptid = __funnelshift_r(w0, w1, sh);
+            ppos = int32_t(__funnelshift_r(w1, w2, sh));
+        } else if (B.row0 > 0) {          // streaming path: the row was written by an earlier launch on this stream
             ptid = uint32_t(t.tid[B.row0 - 1]);
             ppos = t.pos[B.row0 - 1];
         } else {

@@ -126,6 +126,16 @@ int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqu
                         int32_t filteredF, int32_t tspan, int32_t* out, const int64_t* out_offsets);
 void bsg_stage_close(bsg_stage* st);
 
+/*
+ * writeSamAsBamAndIndex (src/bamsignals.cpp:496-534, .Call symbol bamsignals_writeSamAsBamAndIndex,
+ * src/bamsignals_init.c:17): SAM text -> <bampath> (BGZF/BAM) + <bampath>.bai.  Host-only (no device needed).  The
+ * reference goes through htslib's sam_read1 / bam_write1 / bam_index_build and ignores their return values; here
+ * malformed lines are BSG_EFORMAT and input that is not coordinate-sorted is BSG_EUNSORTED (an index over unsorted
+ * records would be wrong).  Positions beyond 2^29 cannot be indexed by a .bai (BSG_EFORMAT); .csi indexes are read
+ * by the counting path but not written here.
+ */
+int bsg_write_sam_as_bam_and_index(const char* sampath, const char* bampath);
+
 const char* bsg_last_error(void);          /* valid until the next call on this thread */
 int  bsg_get_timings(bsg_timings* t);      /* of the last call on this thread */
 int  bsg_device_count(void);               /* CUDA devices visible (0 if none) */

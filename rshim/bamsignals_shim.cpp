@@ -123,3 +123,11 @@ List coverage_core(std::string bampath, RObject& gr, IntegerVector& tlen_filter,
                        maxgap, nullptr, offsets.data(), ptrs.data(), nullptr));
     return res;
 }
+
+// this is used only for the reference's tests (tests/testthat/utils.R:116); same name and signature as
+// src/bamsignals.cpp:498, so src/RcppExports.cpp:71-82 and R/RcppExports.R:20-22 bind it unchanged
+// [[Rcpp::export]]
+bool writeSamAsBamAndIndex(const std::string& sampath, const std::string& bampath) {
+    check(bsg_write_sam_as_bam_and_index(sampath.c_str(), bampath.c_str()));
+    return true;
+}

@@ -145,3 +145,11 @@ def test_gpu_long_contig(tmp_path):
     assert np.array_equal(flat(B.bamProfile(p, gr, binsize=50, ss=True)), flat(O.bamProfile(p, gr, binsize=50, ss=True, mode=O.SCAN)))
     assert np.array_equal(flat(B.bamCoverage(p, gr)), flat(O.bamCoverage(p, gr, mode=O.SCAN)))
     assert int(B.bamCount(p, gr).sum()) > 100
+
+
+def test_cram_is_rejected_by_name(tmp_path):
+    p = str(tmp_path / "x.cram")
+    open(p, "wb").write(b"CRAM\x03\x00" + bytes(64))
+    with pytest.raises(B.BamsignalsError) as e:
+        B.bamCount(p, E.variety_regions())
+    assert e.value.code == -4 and "CRAM input is not supported" in str(e.value)

@@ -6,7 +6,7 @@
 //   of <= 128 symbols: lanes 0 and 16 decode Huffman symbols of their streams into shared-memory token queues, then
 //   all 32 lanes materialise one queue after the other (warp scan of token lengths -> output positions; all literals
 //   of a 32-token chunk in one store; independent short matches replayed concurrently, one lane each).
-// k_crc32: one thread per block, slicing-by-4.
+// k_crc32: one warp per block: 32 slicing-by-4 pieces folded with carry-less multiplies.
 // k_walk<>: one thread per index entry point (BAI linear-index offsets and chunk bounds are record-aligned); each
 //   walks block_size -> next record until the next entry point; a scan of the counts in between gives every walker
 //   its slice of the offsets array (count pass, scan, write pass; no atomics, deterministic order).
@@ -255,14 +255,38 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_crc32: BGZF integrity check on the device (htslib verifies the CRC32 of every inflated block; so do we).
-// One thread per block, slicing-by-4 over the block's bytes with the four 256-entry tables in shared memory.
+// One WARP per block: the block is cut into 32 pieces (lane 0 takes the remainder, the other 31 pieces are equally
+// long), every lane runs slicing-by-4 over its piece, and the 32 registers are folded in a five-level tree:
+// CRC(A || B) = CRC(A) * x^(8 |B|) mod P  xor  CRC(B), where the multiplication is a 32-step carry-less multiply and
+// x^(8 |B|) doubles from level to level.  (One THREAD per block, the first version, walked 64 KiB serially with a
+// 60-cycle dependent chain per word: 2.4 ms for 0.9 GB, 14-20 % of the end-to-end GPU time; this one is ~25x shorter.)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_crc32(const InflateBlock* __restrict__ blocks, const uint32_t* __restrict__ want, int n_blocks,
-                                               const uint8_t* __restrict__ raw, DeviceScalars* sc) {
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+
+// a * b mod P in the reflected representation (bit 31 = x^0), as zlib's multmodp
+__device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        p ^= (a & 0x80000000u) ? b : 0u;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? kCrcPoly : 0u);
+    }
+    return p;
+}
+
+constexpr int kCrcWarps = 4;
+// x^(2^k) mod P for k = 0..19, reflected (x^1 = 0x40000000; each entry is the square of the one before)
+__constant__ uint32_t c_x2n[20] = {0x40000000u, 0x20000000u, 0x08000000u, 0x00800000u, 0x00008000u, 0xedb88320u, 0xb1e6b092u,
+                                   0xa06a2517u, 0xed627daeu, 0x88d14467u, 0xd7bbfe6au, 0xec447f11u, 0x8e7ea170u, 0x6427800eu,
+                                   0x4d47bae0u, 0x09fe548fu, 0x83852d0fu, 0x30362f1au, 0x7b5a9cc3u, 0x31fec169u};
+
+__global__ void __launch_bounds__(kCrcWarps * 32) k_crc32(const InflateBlock* __restrict__ blocks, const uint32_t* __restrict__ want, int n_blocks,
+                                                          const uint8_t* __restrict__ raw, DeviceScalars* sc) {
     __shared__ uint32_t tab[4][256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = uint32_t(i);
-        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? kCrcPoly ^ (c >> 1) : c >> 1;
         tab[0][i] = c;
     }
     __syncthreads();
@@ -271,11 +295,17 @@ __global__ void __launch_bounds__(128) k_crc32(const InflateBlock* __restrict__ 
         for (int t = 1; t < 4; ++t) { c = tab[0][c & 0xffu] ^ (c >> 8); tab[t][i] = c; }
     }
     __syncthreads();
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kCrcWarps + (threadIdx.x >> 5);
     if (b >= n_blocks) return;
     const InflateBlock blk = blocks[b];
-    const uint8_t* p = raw + blk.out_off;
-    uint32_t n = blk.out_len, crc = 0xffffffffu;
+    const uint32_t len = blk.out_len;
+    const uint32_t seg = (len / 32u) & ~3u;      // lanes 1..31: seg bytes each; lane 0: the remaining head
+    const uint32_t head = len - 31u * seg;
+    const uint32_t beg = lane == 0 ? 0u : head + uint32_t(lane - 1) * seg;
+    uint32_t n = lane == 0 ? head : seg;
+    const uint8_t* p = raw + blk.out_off + beg;
+    uint32_t crc = lane == 0 ? 0xffffffffu : 0u;
     while (n && (reinterpret_cast<uintptr_t>(p) & 3)) { crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8); --n; }
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     for (; n >= 4; n -= 4) {
@@ -284,7 +314,17 @@ __global__ void __launch_bounds__(128) k_crc32(const InflateBlock* __restrict__ 
     }
     p = reinterpret_cast<const uint8_t*>(w);
     while (n--) crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8);
-    if (~crc != want[b]) atomicOr(&sc->status, STATUS_BAD_CRC);
+    // fold: at level l the left partner is followed by 2^l pieces of seg bytes
+    uint32_t X = 0x80000000u;                    // x^0
+    for (uint32_t bits = 8u * seg, k = 0; bits; bits >>= 1, ++k)
+        if (bits & 1u) X = crc_mul(c_x2n[k], X);   // x^(8 seg); 8 * seg < 2^20
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        const uint32_t other = __shfl_down_sync(FULL, crc, 1u << l);
+        if ((lane & ((2 << l) - 1)) == 0) crc = crc_mul(crc, X) ^ other;
+        X = crc_mul(X, X);
+    }
+    if (lane == 0 && ~crc != want[b]) atomicOr(&sc->status, STATUS_BAD_CRC);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -369,7 +409,7 @@ void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s) {
     if (n_blocks <= 0) return;
-    k_crc32<<<(n_blocks + 127) / 128, 128, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
+    k_crc32<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
 }
 
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,

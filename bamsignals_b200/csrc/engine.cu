@@ -258,13 +258,37 @@ public:
         tm_.n_devices = 1;
     }
 
+    // The fetch plan (index queries + BGZF header scan) depends only on the regions and `ext`: it can run on its own
+    // thread while the caller builds and uploads the tiles (both take 10-15 ms for 100 k regions).
+    void start_plan(int64_t ext) {
+        if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
+        rg_.sorted_order();                              // lazily cached: compute it before two threads ask for it
+        segs_.clear();
+        plan_err_ = Error{0, ""};
+        plan_ext_ = ext;
+        plan_thread_ = std::thread([this, ext] {
+            const double t0 = now_ms();
+            try { plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_); }
+            catch (Error& e) { plan_err_ = e; }
+            catch (std::exception& e) { plan_err_ = Error{BSG_EARG, std::string("internal error: ") + e.what()}; }
+            plan_ms_ = now_ms() - t0;
+        });
+    }
+
     // Fetch + upload (+ decode unless keep_raw) everything the regions need with halo `ext`.
     void stage(int64_t ext, bool keep_raw) {
         if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
-        const double t0 = now_ms();
+        double t0 = now_ms();
         keep_raw_ = keep_raw;
-        segs_.clear();
-        plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
+        if (plan_thread_.joinable()) {
+            plan_thread_.join();
+            if (plan_err_.code) throw plan_err_;
+            if (plan_ext_ != ext) fail(BSG_EARG, "internal error: plan started with another halo");
+            t0 -= plan_ms_;                              // ms_plan reports the plan's own duration, ms_fetch what follows it
+        } else {
+            segs_.clear();
+            plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
+        }
         const bool gpu = opts_.gpu_inflate >= 0;       // 0 = default = device inflate; -1 = host zlib pool
         const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : (gpu ? kDefaultGpuBatch : kDefaultBatch);
         // group segments into batches
@@ -379,7 +403,7 @@ public:
         std::unique_lock<std::mutex> lk(pf_m_);
         pf_cv_.wait(lk, [&] { return pf_left_ == 0; });
     }
-    ~Session() { stop_streamer(true); wait_prefault(); }
+    ~Session() { if (plan_thread_.joinable()) plan_thread_.join(); stop_streamer(true); wait_prefault(); }
 
     // Tiles depend only on the regions and on (mode, binsize, ss, layout): build + upload them before any device
     // work of the call is queued, and keep them for the next call of a staged session.
@@ -1006,17 +1030,22 @@ private:
                 BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
                 kt_.launches += blocks.empty() ? 0 : 1;
             }
-            Span spw{c.timing_event(), sp.b};
-            BSG_CUDA(cudaEventRecord(spw.a, c.s_comp));
-            walk_spans.push_back(spw);
-            launch_walk(d_raw, c.g_walkers[slot].as<uint2>(), int(walkers.size()), c.g_counts[slot].as<uint32_t>(),
-                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, d_offs, end_pos,
-                        c.scalars.as<DeviceScalars>(), c.s_comp);
             BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
             inflate_spans.push_back(sp);
+            // The record walk stays on the compute stream, between this batch's inflate and the next one's.  (Measured:
+            // on the high-priority stream its three small kernels cannot start while the next inflate holds every SM at
+            // full register occupancy - C2 143 -> 181 ms.)
+            cudaStream_t ws = c.s_comp;
+            Span spw{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(spw.a, ws));
+            launch_walk(d_raw, c.g_walkers[slot].as<uint2>(), int(walkers.size()), c.g_counts[slot].as<uint32_t>(),
+                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, d_offs, end_pos,
+                        c.scalars.as<DeviceScalars>(), ws);
+            BSG_CUDA(cudaEventRecord(spw.b, ws));
+            walk_spans.push_back(spw);
             kt_.launches += (blocks.empty() ? 0 : 1) + (walkers.empty() ? 1 : 3);
-            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, c.s_comp));
-            BSG_CUDA(cudaEventRecord(c.ev_total[slot], c.s_comp));
+            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ws));
+            BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));
             // ---- previous batch: decode ------------------------------------------------------------------------------------------
             tt = now_ms();
             finish(pend);
@@ -1033,7 +1062,7 @@ private:
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
         tm_.ms_h2d = t_copy;
         if (getenv("BSG_DEBUG"))
-            fprintf(stderr, "[bsg] gpu pipeline host ms: descriptors %.1f, slot wait %.1f, memcpy+h2d %.1f, finish(wait total) %.1f; device inflate+walk %.1f (walk %.1f)\n",
+            fprintf(stderr, "[bsg] gpu pipeline host ms: descriptors %.1f, slot wait %.1f, memcpy+h2d %.1f, finish(wait total) %.1f; device inflate %.1f, walk %.1f\n",
                     t_desc, t_wait, t_copy, t_finish, tm_.ms_inflate_gpu, sum_ms(walk_spans));
         BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, c.scalars.p, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
@@ -1074,6 +1103,10 @@ private:
     std::vector<ResidentBatch> resident_;
     int64_t rows_cap_ = 0, n_rows_ = 0;
     bool keep_raw_ = false;
+    std::thread plan_thread_;
+    Error plan_err_{0, ""};
+    int64_t plan_ext_ = 0;
+    double plan_ms_ = 0;
     int resident_chunks_ = 0;
     // background pre-faulting of the caller's output buffer
     std::mutex pf_m_;
@@ -1189,6 +1222,7 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
                     lptr[k] = out ? out + out_offsets[i] : out_ptrs[i];
                 }
                 Session s(bam, std::move(sub), o, o.devices[d]);
+                s.start_plan(ext);
                 s.prepare_tiles(mode, binsize, ss, loff.data());
                 s.begin_count(mode, fp, binsize, ss, ext, nullptr, loff.data(), lptr.data(), true);
                 s.stage(ext, false);
@@ -1271,15 +1305,24 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
                              binsize, ss != 0, ext_pileup(tlen_filter, shift, pe_mid), out, out_offsets, out_ptrs, t0);
             return;
         }
+        const bool dbg = getenv("BSG_DEBUG") != nullptr;
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
+        const double t1 = now_ms();
         const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
+        s.start_plan(ext);
         s.prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
+        const double t2 = now_ms();
         if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
         s.begin_count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, ext, out, out_offsets, out_ptrs, true);
+        const double t3 = now_ms();
         s.stage(ext, false);
+        const double t4 = now_ms();
         s.finish_count();
+        const double t5 = now_ms();
         s.finish_timings(t0);
+        if (dbg) fprintf(stderr, "[bsg] call host ms: open+regions %.1f, tiles %.1f, begin_count %.1f, stage %.1f, finish_count %.1f\n",
+                         t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     });
 }
 
@@ -1298,10 +1341,11 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
             return;
         }
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
+        const int64_t ext = ext_coverage(tlen_filter, tspan);
+        s.start_plan(ext);
         s.prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
         if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
-        const int64_t ext = ext_coverage(tlen_filter, tspan);
         s.begin_count(MODE_COVERAGE, fp, 1, 0, ext, out, out_offsets, out_ptrs, true);
         s.stage(ext, false);
         s.finish_count();

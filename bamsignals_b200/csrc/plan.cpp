@@ -35,11 +35,29 @@ const std::vector<int64_t>& Regions::sorted_order() const {
     for (int64_t i = 1; i < R && sorted; ++i)
         sorted = rid[i - 1] < rid[i] || (rid[i - 1] == rid[i] && loc[i - 1] <= loc[i]);
     if (!sorted) {
-        // sort packed 64-bit keys (rid, loc) with the index as payload: cheaper than an indirect comparator
-        std::vector<std::pair<uint64_t, int64_t>> keyed(R);
-        for (int64_t i = 0; i < R; ++i) keyed[i] = {uint64_t(uint32_t(rid[i])) << 32 | uint32_t(loc[i] ^ int32_t(0x80000000)), i};
-        std::sort(keyed.begin(), keyed.end());
-        for (int64_t i = 0; i < R; ++i) order[i] = keyed[i].second;
+        // Stable LSD radix sort of packed keys (rid, loc) with the index as payload: 11-bit digits over the bits that
+        // are actually used (32 for loc + what the largest rid needs), so 100 k regions take about a millisecond
+        // instead of the 7 ms of a comparison sort.  Ties keep input order, like the (rid, loc, index) key did.
+        struct KV { uint64_t key; int64_t idx; };
+        std::vector<KV> a(R), b(R);
+        uint64_t all = 0;
+        for (int64_t i = 0; i < R; ++i) {
+            a[i] = KV{uint64_t(uint32_t(rid[i])) << 32 | uint32_t(loc[i] ^ int32_t(0x80000000)), i};
+            all |= a[i].key;
+        }
+        int bits = 0;
+        while (bits < 64 && (all >> bits) != 0) ++bits;
+        constexpr int kDigit = 11;
+        std::vector<int64_t> cnt(size_t(1) << kDigit);
+        for (int sh = 0; sh < bits; sh += kDigit) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int64_t i = 0; i < R; ++i) ++cnt[(a[i].key >> sh) & ((1u << kDigit) - 1)];
+            int64_t run = 0;
+            for (auto& c : cnt) { const int64_t t = c; c = run; run += t; }
+            for (int64_t i = 0; i < R; ++i) b[cnt[(a[i].key >> sh) & ((1u << kDigit) - 1)]++] = a[i];
+            a.swap(b);
+        }
+        for (int64_t i = 0; i < R; ++i) order[i] = a[i].idx;
     }
     return order;
 }
@@ -50,6 +68,8 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
     const int mult = ss ? 2 : 1;
     const std::vector<int64_t>& order = rg.sorted_order();
     int64_t cur_region = 0;
+    t->rid.reserve(R); t->loc.reserve(R); t->len.reserve(R); t->strand.reserve(R);
+    t->out_off.reserve(R); t->region.reserve(R); t->ints.reserve(R);
     auto push = [&](int32_t rid, int64_t loc, int64_t len, int32_t strand, int64_t off, int64_t ints) {
         t->rid.push_back(rid); t->loc.push_back(int32_t(loc)); t->len.push_back(int32_t(len));
         t->strand.push_back(strand); t->out_off.push_back(off);
@@ -137,7 +157,9 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         i = j;
     }
     lap("index queries");
-    std::sort(ranges.begin(), ranges.end(), [](const VRange& a, const VRange& b) { return a.beg < b.beg; });
+    // queries were asked in (rid, beg) order, so on a coordinate-sorted file the ranges usually come out sorted already
+    const auto by_beg = [](const VRange& a, const VRange& b) { return a.beg < b.beg; };
+    if (!std::is_sorted(ranges.begin(), ranges.end(), by_beg)) std::sort(ranges.begin(), ranges.end(), by_beg);
     std::vector<VRange> merged;
     for (const VRange& r : ranges) {
         if (r.end <= r.beg) continue;

@@ -270,6 +270,8 @@ def lib():
     L.bsg_coverage_staged.restype = C.c_int
     L.bsg_stage_close.argtypes = [C.c_void_p]
     L.bsg_stage_close.restype = None
+    L.bsg_debug_plan.argtypes = region_args + [C.c_int64, i64p, i64p, i64p, i32p, i32p, C.c_int64]
+    L.bsg_debug_plan.restype = C.c_int64
     L.bsg_write_sam_as_bam_and_index.argtypes = [C.c_char_p, C.c_char_p]
     L.bsg_write_sam_as_bam_and_index.restype = C.c_int
     _lib = L
@@ -293,6 +295,22 @@ def default_opts(**kw) -> BsgOpts:
         else:
             setattr(o, k, v)
     return o
+
+
+def debug_plan(bampath, gr, ext=0, cap=1 << 22) -> dict:
+    """bsg_debug_plan: what the fetch planner decides for `gr` with halo `ext`, and the (tid, pos) of every record inside
+    the planned ranges.  Host-only diagnostic (used by the CPU tests of the index logic); it counts nothing."""
+    m = marshal_regions(gr)
+    nseg, cb, ub = C.c_int64(), C.c_int64(), C.c_int64()
+    tid, pos = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+    n = lib().bsg_debug_plan(os.fsencode(bampath), m.R, m.levels, m.n_levels, _p(m.seq_idx, C.c_int32), _p(m.loc, C.c_int32),
+                             _p(m.width, C.c_int32), _p(m.strand, C.c_int8), int(ext), C.byref(nseg), C.byref(cb), C.byref(ub),
+                             _p(tid, C.c_int32), _p(pos, C.c_int32), cap)
+    if n < 0:
+        _check(int(n))
+    if n > cap:
+        return debug_plan(bampath, gr, ext, int(n))
+    return dict(records=int(n), segments=nseg.value, bytes_compressed=cb.value, bytes_inflated=ub.value, tid=tid[:n], pos=pos[:n])
 
 
 def writeSamAsBamAndIndex(sampath, bampath) -> bool:

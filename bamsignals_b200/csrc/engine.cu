@@ -1437,6 +1437,41 @@ void bsg_shutdown(void) {
     g_bams.clear();
 }
 
+int64_t bsg_debug_plan(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
+                       const int32_t* loc, const int32_t* width, const int8_t* strand, int64_t ext, int64_t* n_segments,
+                       int64_t* bytes_compressed, int64_t* bytes_inflated, int32_t* tid_out, int32_t* pos_out, int64_t cap) {
+    int64_t n_rec = 0;
+    const int rc = guarded([&] {
+        if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");
+        std::shared_ptr<BamFile> bam = open_bam(bampath);
+        Regions rg;
+        resolve_regions(*bam, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg);
+        std::vector<Segment> segs;
+        plan_fetch(*bam, rg, ext, kSegCBytes, get_pool(0), &segs);
+        int64_t cb = 0, ub = 0;
+        Inflater inf;
+        std::vector<uint8_t> buf;
+        for (const Segment& sg : segs) {
+            cb += int64_t(sg.csize); ub += int64_t(sg.usize);
+            buf.resize(sg.usize + 8);
+            uint64_t u = 0;
+            for (const BlockInfo& b : sg.blocks) { inf.inflate_block(bam->data(), b, buf.data() + u, true); u += b.isize; }
+            for (uint64_t p = sg.ubeg; p < sg.uend;) {          // the block_size chain, as the walk kernels follow it
+                if (p + 4 > sg.uend) fail(BSG_EFORMAT, "truncated BAM record in " + bam->path());
+                const int32_t bs = rd_i32(buf.data() + p);
+                if (bs < 32 || p + 4 + uint64_t(bs) > sg.uend) fail(BSG_EFORMAT, "corrupt BAM record chain in " + bam->path());
+                if (n_rec < cap && tid_out && pos_out) { tid_out[n_rec] = rd_i32(buf.data() + p + 4); pos_out[n_rec] = rd_i32(buf.data() + p + 8); }
+                ++n_rec;
+                p += 4 + uint64_t(bs);
+            }
+        }
+        if (n_segments) *n_segments = int64_t(segs.size());
+        if (bytes_compressed) *bytes_compressed = cb;
+        if (bytes_inflated) *bytes_inflated = ub;
+    });
+    return rc == BSG_OK ? n_rec : int64_t(rc);
+}
+
 int bsg_write_sam_as_bam_and_index(const char* sampath, const char* bampath) {
     return guarded([&] {
         // a cached handle of a file this call replaces must not survive it

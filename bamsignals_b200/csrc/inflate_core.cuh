@@ -179,7 +179,7 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint16_t* primary, int bits,
     for (int s = 0; s < n; ++s) cnt[lens[s] & 15]++;
     cnt[0] = 0;
     int left = 1, ok = 1;
-    for (int l = 1; l <= 15; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) ok = 0; }
+    for (int l = 1; l <= 15; ++l) { left = left * 2 - cnt[l]; if (left < 0) { ok = 0; left = 0; } }    // over-subscribed
     int next[16], offs[16];
     next[0] = 0; offs[0] = 0; next[1] = 0; offs[1] = 0;
     for (int l = 1; l < 15; ++l) { next[l + 1] = (next[l] + cnt[l]) << 1; offs[l + 1] = offs[l] + cnt[l]; }

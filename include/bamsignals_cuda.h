@@ -136,6 +136,19 @@ void bsg_stage_close(bsg_stage* st);
  */
 int bsg_write_sam_as_bam_and_index(const char* sampath, const char* bampath);
 
+/*
+ * Diagnostic, host-only (no device needed): runs the fetch planner for the regions with halo `ext` (index queries,
+ * range fusion, segment split, BGZF header scan - what replaces bam_itr_queryi, src/bamsignals.cpp:267) and reports
+ * what it decided: segment count, compressed / inflated bytes, and the (refID, pos) of every record inside the planned
+ * ranges (inflated with zlib and walked on the CPU; at most `cap` are written, all are counted).  It counts nothing:
+ * the CPU test-suite uses it to check the index logic (.bai vs .csi, halos, pruning) without a GPU.
+ * Returns the number of records inside the planned ranges, or a negative BSG_E* code.
+ */
+int64_t bsg_debug_plan(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
+                       const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
+                       int64_t ext, int64_t* n_segments, int64_t* bytes_compressed, int64_t* bytes_inflated,
+                       int32_t* tid_out, int32_t* pos_out, int64_t cap);
+
 const char* bsg_last_error(void);          /* valid until the next call on this thread */
 int  bsg_get_timings(bsg_timings* t);      /* of the last call on this thread */
 int  bsg_device_count(void);               /* CUDA devices visible (0 if none) */

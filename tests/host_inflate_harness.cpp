@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include <zlib.h>
 
@@ -45,6 +47,7 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
             nq = fill_queue(br, ArrayAccess{&T, q}, &op_dec, &eob, &bad);
             if (eob) { phase = 0; if (last) done = 1; }
             if (bad || op_dec > out_len) return 4;
+            if (br.bit_pos() > (uint64_t(in_off) + in_len) * 8) return 6;      // as the kernel: never more than one round past the end
         }
         // phase 2 emulation
         for (int base = 0; base < nq; base += 32) {
@@ -122,8 +125,49 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
     return 0;
 }
 
+// --fuzz N: damage the compressed payload of every block in turn (bit flips, byte runs, truncation) and decode it from a
+// private buffer with the same 4096 bytes of slack the device buffer has.  Any outcome is fine - an error code, a CRC
+// mismatch, even a harmless change - as long as the decode core stays inside its buffers (ASan / UBSan watch) and
+// terminates.
+static int fuzz(const std::vector<uint8_t>& d, size_t n, long iters) {
+    struct Blk { size_t off; uint32_t in_off, in_len, isize, crc; };
+    std::vector<Blk> blks;
+    for (size_t off = 0; off + 28 <= n;) {
+        const uint8_t* h = d.data() + off;
+        const uint32_t xlen = h[10] | h[11] << 8, bs = (h[16] | h[17] << 8) + 1u;
+        Blk b{off, uint32_t(12 + xlen), bs - 12 - xlen - 8, 0, 0};
+        memcpy(&b.isize, h + bs - 4, 4);
+        memcpy(&b.crc, h + bs - 8, 4);
+        if (b.isize) blks.push_back(b);
+        off += bs;
+    }
+    if (blks.empty()) return 0;
+    uint64_t rng = 0x9e3779b97f4a7c15ull;
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    long rejected = 0, crc_caught = 0, harmless = 0;
+    for (long it = 0; it < iters; ++it) {
+        const Blk& b = blks[size_t(it) % blks.size()];
+        std::vector<uint8_t> pb(size_t(b.in_len) + 4096, 0);
+        memcpy(pb.data(), d.data() + b.off + b.in_off, b.in_len);
+        const int kind = int(next() % 4);
+        if (kind == 0) { for (int k = 0, m = 1 + int(next() % 8); k < m; ++k) pb[next() % b.in_len] ^= uint8_t(1u << (next() % 8)); }
+        else if (kind == 1) { size_t a = next() % b.in_len, l = 1 + next() % 64; for (size_t k = a; k < a + l && k < b.in_len; ++k) pb[k] = uint8_t(next()); }
+        else if (kind == 2) { size_t a = next() % b.in_len; memset(pb.data() + a, 0, b.in_len - a); }
+        else { size_t a = next() % std::min<size_t>(b.in_len, 40); pb[a] = uint8_t(next()); }          // block header area
+        std::vector<uint8_t> out(size_t(b.isize) + 64);
+        const int rc = inflate_block(pb.data(), 0, b.in_len, out.data(), b.isize);
+        if (rc) ++rejected;
+        else if (uint32_t(crc32(crc32(0, nullptr, 0), out.data(), b.isize)) != b.crc) ++crc_caught;
+        else ++harmless;
+    }
+    printf("fuzz %ld rejected %ld crc_caught %ld harmless %ld bad 0\n", iters, rejected, crc_caught, harmless);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
+    long fuzz_iters = 0;
+    if (argc >= 4 && strcmp(argv[1], "--fuzz") == 0) { fuzz_iters = atol(argv[2]); argv += 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) return 2;
     std::vector<uint8_t> d;
@@ -133,6 +177,7 @@ int main(int argc, char** argv) {
     fclose(f);
     const size_t n = d.size();
     d.resize(n + 64);
+    if (fuzz_iters > 0) return fuzz(d, n, fuzz_iters);
     size_t off = 0;
     int nb = 0, bad = 0;
     while (off + 28 <= n) {

@@ -45,3 +45,18 @@ def test_deflate_variants(harness, tmp_path, level, straddle, payload):
 def test_generator_output(harness, tmp_path):
     bam, _ = WL.make_bam("c3", 0.002, str(tmp_path), record="realistic")
     assert run(harness, bam) > 10
+
+
+def test_fuzzed_streams_stay_in_bounds(harness, fixture_bam, tmp_path):
+    """Damaged DEFLATE payloads (bit flips, random byte runs, truncation, header bytes): the decode core the GPU kernel
+    shares must reject them, or leave the damage to the CRC32 check, without ever leaving its buffers (ASan / UBSan
+    abort the harness otherwise) and without hanging."""
+    p = str(tmp_path / "v.bam")
+    W.write_bam(p, E.REFS, E.variety_reads(n=1500), block_payload=20000, level=6)
+    for path, n in ((fixture_bam, 1500), (p, 1500)):
+        r = subprocess.run([harness, "--fuzz", str(n), path], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr
+        out = r.stdout.split()
+        assert out[0] == "fuzz" and int(out[1]) == n
+        assert int(out[3]) > n // 2            # most damage is caught by the decoder itself

@@ -1182,24 +1182,35 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
     std::shared_ptr<BamFile> bam = open_bam(bampath);
     Regions rg;
     resolve_regions(*bam, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg);
-    std::vector<int64_t> order(R);
-    for (int64_t i = 0; i < R; ++i) order[i] = i;
+    // Units of the shards are PIECES, not regions: a region with many output ints (C4: 24 whole chromosomes) is cut
+    // into bin-aligned sub-intervals exactly like the counting tiles (make_tiles: each behaves like a region of its own,
+    // DESIGN 3), so that a handful of huge regions still spreads over all devices and the shards balance by reads.
+    HostTiles pc;
+    {
+        const int64_t total_ints = R > 0 ? out_offsets[R] : 0;
+        int64_t piece_ints = std::max<int64_t>(kTileInts, total_ints / (int64_t(nd) * 64));
+        piece_ints = std::min<int64_t>((piece_ints + 7) & ~int64_t(7), int64_t(1) << 30);
+        make_tiles(rg, mode, binsize, ss, out_offsets, int(piece_ints), &pc);
+    }
+    const int64_t P = pc.size();
+    std::vector<int64_t> order(P);
+    for (int64_t i = 0; i < P; ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return rg.rid[a] != rg.rid[b] ? rg.rid[a] < rg.rid[b] : (rg.loc[a] != rg.loc[b] ? rg.loc[a] < rg.loc[b] : a < b);
+        return pc.rid[a] != pc.rid[b] ? pc.rid[a] < pc.rid[b] : (pc.loc[a] != pc.loc[b] ? pc.loc[a] < pc.loc[b] : a < b);
     });
-    // cut points at equal compressed-byte quantiles of the regions' index positions
-    std::vector<int64_t> cut(nd + 1, R);
+    // cut points at equal compressed-byte quantiles of the pieces' index positions (compressed bytes ~ reads)
+    std::vector<int64_t> cut(nd + 1, P);
     cut[0] = 0;
-    if (R > 0) {
-        std::vector<uint64_t> off(R);
-        for (int64_t k = 0; k < R; ++k) off[k] = bam->approx_coffset(rg.rid[order[k]], rg.loc[order[k]]);
-        for (int64_t k = 1; k < R; ++k) off[k] = std::max(off[k], off[k - 1]);
+    if (P > 0) {
+        std::vector<uint64_t> off(P);
+        for (int64_t k = 0; k < P; ++k) off[k] = bam->approx_coffset(pc.rid[order[k]], pc.loc[order[k]]);
+        for (int64_t k = 1; k < P; ++k) off[k] = std::max(off[k], off[k - 1]);
         const uint64_t lo = off.front(), hi = std::max(off.back(), lo + 1);
         for (int d = 1; d < nd; ++d) {
             const uint64_t target = lo + (hi - lo) * uint64_t(d) / uint64_t(nd);
             int64_t c = std::lower_bound(off.begin(), off.end(), target) - off.begin();
-            c = std::max(c, R * d / (4 * nd));                    // never starve a device completely on odd indexes
-            cut[d] = std::max(cut[d - 1], std::min<int64_t>(c, R));
+            c = std::max(c, P * d / (4 * nd));                    // never starve a device completely on odd indexes
+            cut[d] = std::max(cut[d - 1], std::min<int64_t>(c, P));
         }
     }
     get_pool(o.inflate_threads);                                   // create the shared worker pool before the device threads race for it
@@ -1216,10 +1227,10 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
                 std::vector<int64_t> loff(n + 1, 0);
                 std::vector<int32_t*> lptr(n);
                 for (int64_t k = 0; k < n; ++k) {
-                    const int64_t i = order[cut[d] + k];
-                    sub.rid[k] = rg.rid[i]; sub.loc[k] = rg.loc[i]; sub.width[k] = rg.width[i]; sub.strand[k] = rg.strand[i];
-                    loff[k + 1] = loff[k] + (out_offsets[i + 1] - out_offsets[i]);
-                    lptr[k] = out ? out + out_offsets[i] : out_ptrs[i];
+                    const int64_t t = order[cut[d] + k], i = pc.region[t];
+                    sub.rid[k] = pc.rid[t]; sub.loc[k] = pc.loc[t]; sub.width[k] = pc.len[t]; sub.strand[k] = int8_t(pc.strand[t]);
+                    loff[k + 1] = loff[k] + pc.ints[t];
+                    lptr[k] = out ? out + pc.out_off[t] : (out_ptrs[i] ? out_ptrs[i] + (pc.out_off[t] - out_offsets[i]) : nullptr);
                 }
                 Session s(bam, std::move(sub), o, o.devices[d]);
                 s.start_plan(ext);

@@ -107,7 +107,9 @@ def run_ours(args, rank, world, local_rank):
         bam, info = WL.make_bam(preset, gs, d)
     t_gen = time.time() - t_gen
     gr_all, kw, fn = WL.regions(preset, gs)
-    gr, _ = WL.shard_regions(gr_all, rank, world)
+    # bamCount regions own one counter each and cannot be cut; profile / coverage regions are cut into bin-aligned pieces
+    # so that a few huge regions (C4) still balance over the ranks by reads
+    gr, _ = WL.shard_regions(gr_all, rank, world, split_align=None if fn == "bamCount" else int(kw.get("binsize", 1)))
     ca = B.core_args(fn, **kw)
     gpu_inflate = 1 if args.gpu_inflate else -1
     opts = B.default_opts(devices=[local_rank], inflate_threads=max(1, (os.cpu_count() or 1) // world), gpu_inflate=gpu_inflate)

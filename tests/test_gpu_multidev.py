@@ -62,3 +62,25 @@ def test_multi_device_fixture_and_errors(fixture_bam):
     # fewer regions than devices, and empty region sets
     assert B.bamCount(fixture_bam, gr[:1], opts=o).tolist() == O.bamCount(fixture_bam, gr[:1]).tolist()
     assert B.bamCount(fixture_bam, B.GRanges([], [], [], []), opts=o).shape == (0,)
+
+
+def test_multi_device_splits_wide_regions(gen_dir):
+    """A few regions much wider than a shard (C4's shape): the library cuts them into bin-aligned pieces and spreads
+    the pieces over the devices; '+', '-' and '*' regions, strand-specific and binned profiles, and coverage must all
+    come back exactly as one device (and the oracle) computes them."""
+    if ndev() < 2:
+        pytest.skip("needs two GPUs")
+    devs = list(range(min(ndev(), 8)))
+    bam, info = WL.make_bam("c4", 0.002, gen_dir, unplaced=3)
+    lens = WL.contig_lens("c4", 0.002)
+    names = WL.NAMES[:6]
+    gr = B.GRanges(names, [1, 101, 7, 1, 50, 1], [lens[0], lens[1] - 200, lens[2] - 10, lens[3], lens[4] - 100, lens[5]],
+                   ["+", "-", "*", "-", "+", "-"])
+    o = B.default_opts(devices=devs)
+    for kw in (dict(binsize=1, ss=True, shift=30), dict(binsize=7, ss=False), dict(binsize=200, ss=True, paired_end="midpoint", tlenFilter=(70, 200))):
+        got = WL.as_flat(B.bamProfile(bam, gr, opts=o, **kw))
+        assert np.array_equal(got, WL.as_flat(O.bamProfile(bam, gr, nthreads=8, **kw))), kw
+        assert B.timings()["n_devices"] == len(devs)
+    got = WL.as_flat(B.bamCoverage(bam, gr, opts=o, paired_end="extend"))
+    assert np.array_equal(got, WL.as_flat(O.bamCoverage(bam, gr, nthreads=8, paired_end="extend")))
+    assert np.array_equal(B.bamCount(bam, gr, opts=o, ss=True), O.bamCount(bam, gr, ss=True))

@@ -83,3 +83,24 @@ def test_shards_partition_the_regions():
     for world in (1, 2, 3, 8):
         seen = np.concatenate([WL.shard_regions(gr, r, world)[1] for r in range(world)])
         assert np.array_equal(np.sort(seen), np.arange(len(gr)))
+
+
+def test_split_wide_regions_concatenates(tmp_path):
+    """bench.py shards profile / coverage configs by bin-aligned PIECES of wide regions (tools/workloads.py
+    split_wide_regions; the library does the same inside a multi-device call): the pieces' results, concatenated in
+    5' -> 3' order, must be the regions' results for '+', '-' and '*' regions."""
+    import bamsignals_b200 as B
+    import oracle_api as O
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import workloads as WL
+    bam, _ = WL.make_bam("c4", 0.002, str(tmp_path))
+    lens = WL.contig_lens("c4", 0.002)
+    gr = B.GRanges(WL.NAMES[:4], [1, 101, 7, 1], [lens[0], lens[1] - 200, lens[2] - 10, lens[3]], ["+", "-", "*", "-"])
+    for bs, kw in ((200, dict(paired_end="midpoint", tlenFilter=(70, 200))), (7, dict(ss=True)), (1, dict(ss=True, shift=30))):
+        pieces = WL.split_wide_regions(gr, 8, bs)
+        assert len(pieces) > 8 * len(gr)
+        assert np.array_equal(WL.as_flat(O.bamProfile(bam, pieces, binsize=bs, **kw)), WL.as_flat(O.bamProfile(bam, gr, binsize=bs, **kw)))
+    assert np.array_equal(WL.as_flat(O.bamCoverage(bam, WL.split_wide_regions(gr, 8, 1), paired_end="extend")),
+                          WL.as_flat(O.bamCoverage(bam, gr, paired_end="extend")))
+    parts = [WL.shard_regions(gr, r, 4, split_align=200)[0] for r in range(4)]
+    assert sum(len(p) for p in parts) == len(WL.split_wide_regions(gr, 4, 200))

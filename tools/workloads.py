@@ -93,11 +93,36 @@ def as_flat(result):
     return np.concatenate([s.ravel(order="F") for s in sig])
 
 
-def shard_regions(gr, rank, world):
+def split_wide_regions(gr, world, align=1):
+    """Cut regions that are much wider than a rank's share into pieces of a multiple of `align` bp (the bin size),
+    counted from the region's 5' end (start for '+' / '*', end for '-'): each piece behaves like a region of its own
+    and the pieces' results, concatenated in 5' -> 3' order, are the region's result.  A config with a few
+    huge regions (C4: 24 whole contigs) can then be balanced over the ranks by reads instead of by region count."""
+    total = int(gr.width.astype(np.int64).sum())
+    piece = max(align, -(-(total // (world * 64) + 1) // align) * align)
+    ci, start, width, strand = [], [], [], []
+    for i in range(len(gr)):
+        w, s0, st, c = int(gr.width[i]), int(gr.start[i]), int(gr.strand[i]), int(gr.seq_idx[i])
+        if w <= 2 * piece:
+            ci.append(c); start.append(s0); width.append(w); strand.append(st)
+            continue
+        for lo in range(0, w, piece):
+            pw = min(piece, w - lo)
+            ci.append(c); width.append(pw); strand.append(st)
+            start.append(s0 + w - lo - pw if st < 0 else s0 + lo)
+    return GRanges.from_codes(gr.seqlevels, np.asarray(ci, np.int32), np.asarray(start, np.int64), np.asarray(width, np.int64),
+                              np.asarray(strand, np.int8))
+
+
+def shard_regions(gr, rank, world, split_align=None):
     """Contiguous slice (in (chromosome, start) order) of the region set for this rank -> (GRanges, original indices).
-    Regions are independent: no exchange step, every output element has exactly one owner."""
+    Regions are independent: no exchange step, every output element has exactly one owner.
+    split_align (a bin size): wide regions are first cut into bin-aligned pieces (split_wide_regions); the returned
+    indices then refer to the pieces."""
     if world == 1:
         return gr, np.arange(len(gr))
+    if split_align:
+        gr = split_wide_regions(gr, world, int(split_align))
     order = np.lexsort((gr.start, gr.seq_idx))
     lo, hi = len(gr) * rank // world, len(gr) * (rank + 1) // world
     idx = np.sort(order[lo:hi])

@@ -71,13 +71,18 @@ __device__ __forceinline__ Decoded decode_one(const LD& ld, uint32_t o, uint32_t
     if (c + 4u * n_cigar > rec_end) {
         d.bad = STATUS_CORRUPT;
     } else if (!(flag & 0x4u) && n_cigar) {             // bam_endpos: unmapped reads have no reference length
+        // nine reads in ten have a one-operation CIGAR: that case is straight-line code; the rest take a plain loop
+        // (unrolled by eight, the loop's remainder ladder cost a one-op read 45 instructions)
         const uint32_t cb = c & ~3u, csh = (c & 3u) * 8;
-        uint32_t lo = ld(cb);
-        for (uint32_t k = 0; k < n_cigar; ++k) {
-            const uint32_t hi = ld(cb + 4 * k + 4);
-            const uint32_t op = __funnelshift_r(lo, hi, csh);
+        uint32_t lo = ld(cb), hi = ld(cb + 4);
+        uint32_t op = __funnelshift_r(lo, hi, csh);
+        rlen = ((0x18Du >> (op & 0xfu)) & 1u) ? op >> 4 : 0u;    // M, D, N, =, X consume the reference
+#pragma unroll 1
+        for (uint32_t k = 1; k < n_cigar; ++k) {
             lo = hi;
-            if ((0x18Du >> (op & 0xfu)) & 1u) rlen += op >> 4;   // M, D, N, =, X consume the reference
+            hi = ld(cb + 4 * k + 4);
+            op = __funnelshift_r(lo, hi, csh);
+            if ((0x18Du >> (op & 0xfu)) & 1u) rlen += op >> 4;
         }
     }
     if (rlen == 0) rlen = 1;
@@ -110,7 +115,8 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
     extern __shared__ __align__(128) uint8_t sm_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_lo, s_bytes;
-    __shared__ int s_kept, s_arrived, s_ghlo, s_ghhi;
+    __shared__ int s_hlo, s_hhi, s_ghlo, s_ghhi;
+    __shared__ int2 s_last[kThreads / 32];         // (tid, pos) of every warp's last record
     // which batch does this chunk belong to?
     DecodeBatch B = single;
     int bi = 0;
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
         } else {
             s_lo = 0; s_bytes = 0;
         }
-        s_kept = 0; s_arrived = 0;
+        s_hlo = INT_MIN; s_hhi = INT_MIN;
         // the running halo maxima, read ONCE per CTA (L2, in flight during the copy) and handed to the warps through
         // shared memory: a warp whose own maxima do not beat them has nothing to publish, and a stale value only costs
         // a redundant atomicMax.  (Every warp reading them itself put 3.6 M loads on one L2 line: +0.35 ms.)
@@ -195,16 +201,26 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
         t.c0[row] = o0;
         t.c1[row] = o1;
     }
-    // coordinate-sortedness: compare with the previous record (previous lane; lane 0 re-reads it)
+    // One barrier serves the cross-warp sortedness check and the CTA-wide statistics: before it, every warp leaves the
+    // key of its last record and its halo maxima in shared memory; the barrier itself counts the kept reads.
+    const int wid = threadIdx.x >> 5;
+    hlo = __reduce_max_sync(FULL, hlo);
+    hhi = __reduce_max_sync(FULL, hhi);
+    if (lane == 31) s_last[wid] = make_int2(d.tid, d.pos);
+    if (lane == 0 && hlo != INT_MIN) { atomicMax(&s_hlo, hlo); atomicMax(&s_hhi, hhi); }
     uint32_t ptid = __shfl_up_sync(FULL, uint32_t(d.tid), 1);
     int32_t ppos = __shfl_up_sync(FULL, d.pos, 1);
+    const int kept_cta = __syncthreads_count(keep);
+    // coordinate-sortedness: compare with the previous record (previous lane; lane 0 takes the previous warp's last
+    // record; thread 0 re-reads the record before the chunk)
     bool have_prev = active;
     if (lane == 0 && active) {
-        if (i > 0) {
+        if (threadIdx.x > 0) {
+            const int2 l = s_last[wid - 1];
+            ptid = uint32_t(l.x); ppos = l.y;
+        } else if (i > 0) {
             const uint32_t a = __ldg(B.offs + i - 1) + 4, b = a & ~3u, sh = (a & 3u) * 8;
-            uint32_t w0, w1, w2;
-            if (staged && threadIdx.x > 0) { w0 = sld(b); w1 = sld(b + 4); w2 = sld(b + 8); }
-            else { w0 = gld(b); w1 = gld(b + 4); w2 = gld(b + 8); }
+            const uint32_t w0 = gld(b), w1 = gld(b + 4), w2 = gld(b + 8);
             ptid = __funnelshift_r(w0, w1, sh);
             ppos = int32_t(__funnelshift_r(w1, w2, sh));
         } else if (table && bi > 0) {
@@ -226,24 +242,13 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
     uint32_t bad = d.bad;
     if (have_prev && (uint32_t(d.tid) < ptid || (uint32_t(d.tid) == ptid && d.pos < ppos))) bad |= STATUS_UNSORTED;
     if (bad) atomicOr(&sc->status, bad);
-    // Halo maxima and the kept-read count.  One redux per warp; the maxima go out only when they beat the value read at
-    // the start.  The count is summed per CTA in shared memory and the LAST warp to arrive publishes it (no block-level
-    // barrier: warps retire independently) into one of kKeptSlots counters that sit on different 128-byte lines -
-    // atomics on one line serialise in its L2 slice (measured: 1.8 M same-line atomics cost this kernel 3.7 ms).
-    hlo = __reduce_max_sync(FULL, hlo);
-    hhi = __reduce_max_sync(FULL, hhi);
-    const int kept = __popc(__ballot_sync(FULL, keep));
-    if (lane == 0) {
-        if (kept) {
-            if (hlo > s_ghlo) atomicMax(&sc->halo_lo, hlo);
-            if (hhi > s_ghhi) atomicMax(&sc->halo_hi, hhi);
-            atomicAdd(&s_kept, kept);
-        }
-        __threadfence_block();
-        if (atomicAdd(&s_arrived, 1) == kThreads / 32 - 1) {
-            const int tot = *reinterpret_cast<volatile int*>(&s_kept);
-            if (tot) atomicAdd(&sc->kept[(blockIdx.x & (kKeptSlots - 1)) * kKeptStride], (unsigned long long)tot);
-        }
+    // halo maxima and the kept-read count: published once per CTA, the maxima only when they beat the value read at the
+    // start, the count into one of kKeptSlots counters that sit on different 128-byte lines (atomics on one line
+    // serialise in its L2 slice: 1.8 M same-line atomics cost this kernel 3.7 ms)
+    if (threadIdx.x == 0 && kept_cta) {
+        if (s_hlo > s_ghlo) atomicMax(&sc->halo_lo, s_hlo);
+        if (s_hhi > s_ghhi) atomicMax(&sc->halo_hi, s_hhi);
+        atomicAdd(&sc->kept[(blockIdx.x & (kKeptSlots - 1)) * kKeptStride], (unsigned long long)kept_cta);
     }
 }
 

@@ -57,11 +57,13 @@ extern "C" {
 /* Execution options; none of them changes results.  Zero-initialise, set struct_size = sizeof(bsg_opts). */
 typedef struct bsg_opts {
     int32_t struct_size;
-    int32_t n_devices;        /* 0 = device 0 only; 1..16 = devices[0..n): regions are sharded over the devices inside the
-                                 call, one host thread + pipeline per device, no collective */
+    int32_t n_devices;        /* 0 = device 0 only; 1..16 = devices[0..n): regions (wide ones cut into bin-aligned pieces)
+                                 are sharded over the devices inside the call, balanced by the compressed bytes between
+                                 their index positions; one host thread + pipeline per device, no collective */
     int32_t devices[16];
     int32_t inflate_threads;  /* host inflate / record-walk workers; 0 = all hardware threads */
-    int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (1 GiB device inflate, 64 MiB host) */
+    int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (1 GiB device inflate with a first batch
+                                 of a quarter of that, 64 MiB host) */
     int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does); on by default */
     int32_t use_cache;        /* reserved, must be 0 (open BAM handles and buffers are always reused across calls;
                                  record data is never cached: every call reads, inflates and decodes the file again) */

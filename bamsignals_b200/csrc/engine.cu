@@ -280,6 +280,7 @@ public:
         if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
         double t0 = now_ms();
         keep_raw_ = keep_raw;
+        staged_ext_ = ext;
         if (plan_thread_.joinable()) {
             plan_thread_.join();
             if (plan_err_.code) throw plan_err_;
@@ -358,6 +359,15 @@ public:
         }
         run_pipeline();
         tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
+    }
+
+    // A staged call may only look as far around its regions as the session fetched: the reference widens every index
+    // query by `ext` (src/bamsignals.cpp:255-256,457,487); with a smaller halo, reads near the region borders would
+    // silently be missing.
+    void require_ext(int64_t ext) const {
+        if (ext > staged_ext_)
+            fail(BSG_EARG, "this call needs a halo of " + std::to_string(ext) + " bp around the regions, the session was staged with ext_hint = " +
+                           std::to_string(staged_ext_));
     }
 
     // Staged sessions: decode + filter every resident raw batch again (K1) in ONE launch, timed.
@@ -1103,6 +1113,7 @@ private:
     std::vector<ResidentBatch> resident_;
     int64_t rows_cap_ = 0, n_rows_ = 0;
     bool keep_raw_ = false;
+    int64_t staged_ext_ = 0;
     std::thread plan_thread_;
     Error plan_err_{0, ""};
     int64_t plan_ext_ = 0;
@@ -1397,7 +1408,7 @@ int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual
     return guarded([&] {
         const double t0 = now_ms();
         st->s->reset_counters();
-        (void)ext_pileup(tlen_filter, shift, pe_mid);
+        st->s->require_ext(ext_pileup(tlen_filter, shift, pe_mid));
         st->s->prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
         st->s->decode_resident(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp);
@@ -1412,7 +1423,7 @@ int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqu
     return guarded([&] {
         const double t0 = now_ms();
         st->s->reset_counters();
-        (void)ext_coverage(tlen_filter, tspan);
+        st->s->require_ext(ext_coverage(tlen_filter, tspan));
         st->s->prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
         st->s->decode_resident(MODE_COVERAGE, fp);

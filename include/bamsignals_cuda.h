@@ -116,7 +116,10 @@ int64_t bsg_output_layout(int64_t R, const int32_t* width, int32_t binsize, int3
  * bsg_stage() fetches, inflates and uploads the byte ranges a region set needs and keeps the RAW record bytes and
  * record offsets resident in HBM.  bsg_pileup_staged()/bsg_coverage_staged() then run the device path only
  * (decode -> filter -> join -> count) and leave the result on the device unless `out` is given.  This is how the
- * kernel-only throughput is measured, and how an application amortises inflate over many parameter settings. */
+ * kernel-only throughput is measured, and how an application amortises inflate over many parameter settings.
+ * ext_hint is the halo fetched around every region, the `ext` of src/bamsignals.cpp:457,487: a staged call needs
+ * |shift| (+ tlen_filter[1] when pe_mid) for pileups and tlen_filter[1] when tspan for coverage; a call that needs
+ * more than the session was staged with is refused with BSG_EARG instead of silently missing reads. */
 typedef struct bsg_stage bsg_stage;
 int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
                    const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,

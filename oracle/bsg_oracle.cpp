@@ -131,7 +131,8 @@ private:
         b.data.resize(isize);
         inflateReset(&zs_);
         zs_.next_in = cbuf_.data(); zs_.avail_in = uInt(cbuf_.size() - 8);
-        zs_.next_out = b.data.data(); zs_.avail_out = isize;
+        uint8_t none = 0;                                   // zlib rejects a null next_out, even for the empty EOF block
+        zs_.next_out = isize ? b.data.data() : &none; zs_.avail_out = isize;
         int rc = inflate(&zs_, Z_FINISH);
         if (!(rc == Z_STREAM_END && zs_.avail_out == 0)) fail("BGZF inflate failed");
         if (uint32_t(crc32(crc32(0, nullptr, 0), b.data.data(), isize)) != crc) fail("BGZF CRC mismatch");
@@ -416,6 +417,10 @@ inline void apply(const Params& P, const ReadState& st, Region& g) {
         if (P.ss) ++g.out[2 * (rel / P.binsize) + anti]; else ++g.out[rel / P.binsize];
     } else {                                                     // src/bamsignals.cpp:418-438
         if (st.s >= g.end() || st.e < g.loc) return;
+        // Deliberate difference: for a ZERO-WIDTH region the reference's test above (:420) still passes for a read that
+        // spans `loc`, and :424/:432 then increment array[0] of an empty vector - a write past the end of the R
+        // object.  The defined result is the empty vector; nothing is written here.
+        if (g.len <= 0) return;
         if (g.strand >= 0) {
             int64_t p = st.s - g.loc; ++g.out[p > 0 ? p : 0];
             p = st.e + 1 - g.loc; if (p < g.len) --g.out[p];

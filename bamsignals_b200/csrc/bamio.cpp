@@ -245,13 +245,28 @@ void BamFile::load_index() {
     need(4);
     const int32_t n_ref = rd_i32(d.data() + p);
     p += 4;
-    if (n_ref < 0) fail(BSG_EFORMAT, "corrupt BAM index for " + path_);
+    // every reference takes at least its n_bin field (and n_intv in a BAI): a count the file cannot hold is garbage,
+    // and must not size an allocation
+    if (n_ref < 0 || uint64_t(n_ref) * (csi ? 4 : 8) > d.size() - p) fail(BSG_EFORMAT, "corrupt BAM index for " + path_);
     const uint32_t first_leaf = uint32_t(((1ull << (3 * depth_)) - 1) / 7), n_leaf = 1u << (3 * depth_);
     meta_bin_ = uint32_t(((1ull << (3 * (depth_ + 1))) - 1) / 7) + 1;                      // 37450 for a BAI
     refs_.resize(n_ref);
     entries_.push_back(first_rec_);
+    // Per-window arrays (CSI: rebuilt linear index; both: leaf bins) are sized by bin NUMBERS found in the file.  A
+    // window far behind the end of its contig cannot matter to a query (dropping it only loosens the fetched range,
+    // which stays a superset), so such entries are ignored instead of sizing an array; the total is bounded too.
+    uint64_t windows_total = 0;
+    const auto window_cap = [&](int r) {
+        const uint64_t len = r < int(lens_.size()) && lens_[r] > 0 ? uint64_t(lens_[r]) : 0;
+        return std::min<uint64_t>(uint64_t(1) << 24, (len >> min_shift_) + 4097);
+    };
+    const auto account = [&](uint64_t grown) {
+        windows_total += grown;
+        if (windows_total > (uint64_t(1) << 27)) fail(BSG_EFORMAT, "unsupported index geometry (too many windows) for " + path_);
+    };
     for (int r = 0; r < n_ref; ++r) {
         RefIndex& ri = refs_[r];
+        const uint64_t w_cap = window_cap(r);
         need(4);
         int32_t n_bin = rd_i32(d.data() + p);
         p += 4;
@@ -289,18 +304,22 @@ void BamFile::load_index() {
                 uint32_t first = 0;
                 while (l < depth_ && bin >= first + (1u << (3 * l))) { first += 1u << (3 * l); ++l; }
                 const uint64_t w = uint64_t(bin - first) << (3 * (depth_ - l));
-                if (ri.linear.size() <= w) ri.linear.resize(w + 1, 0);
-                ri.linear[w] = ri.linear[w] ? std::min(ri.linear[w], loff) : loff;
+                if (w < w_cap) {
+                    if (ri.linear.size() <= w) { account(w + 1 - ri.linear.size()); ri.linear.resize(w + 1, 0); }
+                    ri.linear[w] = ri.linear[w] ? std::min(ri.linear[w], loff) : loff;
+                }
                 entries_.push_back(loff);
             }
             if (bin >= first_leaf) {
                 // Leaf bins go into a flat per-window array: the file is coordinate-sorted, so the chunks of a run of
                 // consecutive leaf bins lie between the first bin's first chunk and the last bin's last chunk.
                 const size_t w = bin - first_leaf;
-                if (ri.leaf.size() <= w) ri.leaf.resize(w + 1, VRange{0, 0});
-                VRange lr{~0ull, 0};
-                for (auto& c : cs) { lr.beg = std::min(lr.beg, c.beg); lr.end = std::max(lr.end, c.end); }
-                if (lr.end > lr.beg) ri.leaf[w] = lr;
+                if (w < w_cap) {
+                    if (ri.leaf.size() <= w) { account(w + 1 - ri.leaf.size()); ri.leaf.resize(w + 1, VRange{0, 0}); }
+                    VRange lr{~0ull, 0};
+                    for (auto& c : cs) { lr.beg = std::min(lr.beg, c.beg); lr.end = std::max(lr.end, c.end); }
+                    if (lr.end > lr.beg) ri.leaf[w] = lr;
+                }
             } else {
                 ri.bins[bin] = std::move(cs);
             }

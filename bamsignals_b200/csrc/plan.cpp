@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 #include <numeric>
 
@@ -187,6 +188,10 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         for (int64_t k = a; k < b; ++k) {
             try { scan_segment(bam, &(*segs)[k]); }
             catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }
+            catch (std::exception& e) {          // nothing may escape a pool thread
+                std::lock_guard<std::mutex> g(em);
+                if (!first.code) first = Error{BSG_ENOMEM, std::string("block scan failed: ") + e.what()};
+            }
         }
     });
     lap("block scan");

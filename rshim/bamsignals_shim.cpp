@@ -10,8 +10,10 @@
 // The per-region htslib loops (overlapAndPileup, :240-291) and cumsum (:464-470) are replaced by ONE call into the
 // C ABI of include/bamsignals_cuda.h.
 //
-// STATUS: source only.  R, Rcpp and Rhtslib are not installable offline, so this file has never been compiled;
-// the same C ABI is exercised from Python (bamsignals_b200/api.py) by the parity tests.
+// STATUS: R, Rcpp and Rhtslib are not installable offline, so the R package has not been built with this file.  It IS
+// compiled and run by tests/test_zz_rshim_mock.py against a minimal stand-in for <Rcpp.h> (tests/mock_rcpp/): the
+// arguments it passes through the C ABI, the layout it returns and the errors it re-raises are checked there; the same
+// C ABI is exercised from Python (bamsignals_b200/api.py) by the parity tests.
 #include <Rcpp.h>
 
 #include <string>

@@ -30,12 +30,22 @@ def stub_driver(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
-def real_driver(tmp_path_factory):
-    exe = str(tmp_path_factory.mktemp("rshim") / "driver_real")
-    libdir = os.path.join(ROOT, "bamsignals_b200")
-    r = subprocess.run(COMMON + ["-L", libdir, "-lbamsignals_cuda", f"-Wl,-rpath,{libdir}", "-o", exe], capture_output=True, text=True)
-    if r.returncode != 0:
-        pytest.skip("cannot link the shim against libbamsignals_cuda.so here: " + r.stderr[-300:])
+def real_driver():
+    """Built in-tree (tests/_build/, git-ignored) under a name that hashes its sources, so that a binary built on the
+    CPU box travels to the GPU box with the snapshot and is reused there; $ORIGIN keeps the rpath relocatable."""
+    import hashlib
+    srcs = COMMON[-2:] + [os.path.join(ROOT, "tests", "mock_rcpp", "Rcpp.h"), os.path.join(ROOT, "include", "bamsignals_cuda.h")]
+    h = hashlib.sha1(b"".join(open(f, "rb").read() for f in srcs)).hexdigest()[:12]
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, f"rshim_driver_real_{h}")
+    if not os.path.exists(exe):
+        libdir = os.path.join(ROOT, "bamsignals_b200")
+        r = subprocess.run(COMMON + ["-L", libdir, "-lbamsignals_cuda", "-Wl,-rpath,$ORIGIN/../../bamsignals_b200", "-o", exe + ".tmp"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("cannot link the shim against libbamsignals_cuda.so here: " + r.stderr[-300:])
+        os.replace(exe + ".tmp", exe)
     return exe
 
 

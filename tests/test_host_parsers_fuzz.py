@@ -42,7 +42,7 @@ def seeds(tmp_path_factory):
 
 def run(exe, bam, ext=50):
     env = dict(os.environ, ASAN_OPTIONS="max_allocation_size_mb=3072:allocator_may_return_null=0:detect_leaks=1")
-    r = subprocess.run([exe, bam, str(ext)], capture_output=True, text=True, timeout=60, env=env)
+    r = subprocess.run([exe, bam, str(ext)], capture_output=True, text=True, errors="replace", timeout=60, env=env)
     assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-3000:])
     assert r.stdout.startswith("ok ") or r.stdout.startswith("error -"), r.stdout
     return r.stdout
@@ -146,3 +146,62 @@ def test_crafted_headers(harness, tmp_path):
     io = outs[len(cases):]
     assert io[0].startswith("ok refs 1 ") and io[7].startswith("ok refs 1 ")      # io[7]: a far-away leaf bin is ignored
     assert all(o.startswith("error -4") for o in io[1:7] + io[8:]), io
+
+
+# ---- the SAM -> BAM + BAI writer (bamwrite.cpp) --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def writer_harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("writerharness") / "writer_harness")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-o", exe, os.path.join(ROOT, "tests", "host_writer_harness.cpp"), os.path.join(CSRC, "bamwrite.cpp"), "-lz"])
+    return exe
+
+
+SAM = ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chrA\tLN:100000\n@SQ\tSN:chrB\tLN:5000\n"
+       "r1\t99\tchrA\t100\t30\t5S20M3D2I10M\t=\t300\t250\tACGTACGTACGTACGTACGTACGTACGTACGTACGTA\tIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\tNM:i:3\tXS:Z:hello\tXA:A:c\tXF:f:1.5\tXB:B:c,1,-2,3\n"
+       "r2\t147\tchrA\t300\t30\t30M\t=\t100\t-250\t*\t*\tXH:H:1AE3\tXI:B:I,70000,1\n"
+       "r3\t16\tchrA\t70000\t0\t10M5000N10M\t*\t0\t0\t*\t*\n"
+       "r4\t0\tchrB\t1\t255\t*\t*\t0\t0\t*\t*\n"
+       "r5\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t!!!!\n")
+
+
+def run_writer(exe, sam, bam):
+    env = dict(os.environ, ASAN_OPTIONS="max_allocation_size_mb=3072:detect_leaks=1")
+    r = subprocess.run([exe, sam, bam], capture_output=True, text=True, errors="replace", timeout=60, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-3000:])
+    assert r.stdout.startswith("ok") or r.stdout.startswith("error -"), r.stdout
+    return r.stdout
+
+
+def test_writer_on_mutated_sam(writer_harness, harness, tmp_path):
+    sam, bam = str(tmp_path / "m.sam"), str(tmp_path / "m.bam")
+    open(sam, "w").write(SAM)
+    assert run_writer(writer_harness, sam, bam).startswith("ok")
+    assert run(harness, bam).startswith("ok refs 2 ") and " records 4" in run(harness, bam)    # our reader accepts our writer's output
+    rng = np.random.default_rng(23)
+    raw = SAM.encode()
+    tokens = [b"\t", b"\n", b"*", b"-", b"99999999999999999999", b"2147483648", b"-2147483649", b"0M", b"65536M", b"=", b"@SQ\tSN:chrA\tLN:-1\n",
+              b"XX:B:i,", b"XX:Z:", b"XX:i:", b"", b"\x00", b"\xff", b"chrB", b"chrC", b"536870913", b"1S" * 40000]
+    refused = 0
+    for k in range(250):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 4))
+            o = int(rng.integers(0, len(b)))
+            if kind == 0:
+                b[o] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del b[o:o + int(rng.integers(1, 12))]
+            elif kind == 2:
+                b[o:o] = tokens[int(rng.integers(0, len(tokens)))]
+            else:                                   # swap two lines (unsorted input must be refused, not indexed)
+                lines = bytes(b).split(b"\n")
+                i, j = int(rng.integers(0, len(lines))), int(rng.integers(0, len(lines)))
+                lines[i], lines[j] = lines[j], lines[i]
+                b = bytearray(b"\n".join(lines))
+        open(sam, "wb").write(bytes(b))
+        out = run_writer(writer_harness, sam, bam)
+        refused += out.startswith("error")
+        if out.startswith("ok"):                    # whatever the writer accepts, the reader must be able to plan
+            assert run(harness, bam).startswith("ok"), bytes(b)
+    assert refused > 25

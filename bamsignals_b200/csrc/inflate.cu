@@ -40,6 +40,10 @@ constexpr int kQ2Warps = 4;
 #ifndef BSG_Q2_MINB
 #define BSG_Q2_MINB 7
 #endif
+// Warps per CTA by streams per warp: the static shared memory of a CTA (warps x streams x 3.7 KB) must stay below 48 KB,
+// and 7 CTAs per SM must keep 56 streams resident either way.  The four-stream instantiation is an EXPERIMENT (round 2:
+// BSG_INFLATE_STREAMS=4): four serial decode chains share phase 1's instructions instead of two, at half the warps.
+template <int kStreams> struct Q2Cfg { static constexpr int kWarps = kStreams == 4 ? 2 : kQ2Warps; };
 struct Q2Smem {
     inflate_core::Tables T;
     uint32_t q[inflate_core::kQueue];
@@ -170,16 +174,18 @@ __device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int 
 }
 
 template <int kStreams>
-__global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
+__global__ void __launch_bounds__(Q2Cfg<kStreams>::kWarps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
                                                                   const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
-    static_assert(kStreams == 1 || kStreams == 2, "one or two streams per warp");
-    __shared__ Q2Smem s_mem[kQ2Warps][kStreams];
+    static_assert(kStreams == 1 || kStreams == 2 || kStreams == 4, "one, two or four streams per warp");
+    constexpr int kWarps = Q2Cfg<kStreams>::kWarps;
+    constexpr int kLanes = 32 / kStreams;                    // lanes per stream in phase 1; the first of them decodes
+    __shared__ Q2Smem s_mem[kWarps][kStreams];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = kStreams == 2 ? lane >> 4 : 0;          // the stream this lane belongs to in phase 1
-    const bool dec = kStreams == 2 ? (lane & 15) == 0 : lane == 0;      // lanes 0 (and 16) decode
-    const int b = (blockIdx.x * kQ2Warps + wid) * kStreams + sub;
-    if ((blockIdx.x * kQ2Warps + wid) * kStreams >= n_blocks) return;       // whole warp idle
+    const int sub = kStreams > 1 ? lane / kLanes : 0;        // the stream this lane belongs to in phase 1
+    const bool dec = kStreams > 1 ? (lane & (kLanes - 1)) == 0 : lane == 0;      // lanes 0 (and 16; or 0, 8, 16, 24) decode
+    const int b = (blockIdx.x * kWarps + wid) * kStreams + sub;
+    if ((blockIdx.x * kWarps + wid) * kStreams >= n_blocks) return;       // whole warp idle
     Tables& T = s_mem[wid][sub].T;
     volatile uint32_t* q = s_mem[wid][sub].q;
     SmemAccess acc{uint32_t(__cvta_generic_to_shared(s_mem[wid][sub].T.lit)), 0u, 0u};
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const
         // ---- phase 2: materialise the two queues, one after the other, with the whole warp ------------------------------
 #pragma unroll
         for (int s = 0; s < kStreams; ++s) {
-            const int src = 16 * s;
+            const int src = kLanes * s;
             const int st_s = __shfl_sync(FULL, state, src);
             const int nq_s = __shfl_sync(FULL, nq, src);
             const uint32_t pb_s = __shfl_sync(FULL, pos_base, src);
@@ -398,12 +404,16 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s) {
     if (n_blocks <= 0) return;
-    // BSG_INFLATE_STREAMS=1 selects the one-stream-per-warp instantiation (kept for A/B measurements)
-    const int streams = (getenv("BSG_INFLATE_STREAMS") && atoi(getenv("BSG_INFLATE_STREAMS")) == 1) ? 1 : 2;
-    const int per_cta = kQ2Warps * streams;
+    // BSG_INFLATE_STREAMS=1 / 4 select the one- / four-streams-per-warp instantiations (A/B measurements only; the
+    // four-stream one has not been on a GPU yet); anything else is the production kernel with two streams per warp
+    const int want = getenv("BSG_INFLATE_STREAMS") ? atoi(getenv("BSG_INFLATE_STREAMS")) : 2;
+    const int streams = want == 1 ? 1 : (want == 4 ? 4 : 2);
+    const int warps = streams == 4 ? Q2Cfg<4>::kWarps : kQ2Warps;
+    const int per_cta = warps * streams;
     const int grid = (n_blocks + per_cta - 1) / per_cta;
-    if (streams == 1) k_inflate_q2<1><<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else k_inflate_q2<2><<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    if (streams == 1) k_inflate_q2<1><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    else if (streams == 4) k_inflate_q2<4><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    else k_inflate_q2<2><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
 }
 
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,

@@ -33,14 +33,23 @@ def main():
         variants.append((label, dict(e.split("=", 1) for e in envs.split(",") if e)))
     keys = sorted({k for _, e in variants for k in e})
     res = {label: [] for label, _ in variants}
+    first_result = None
     for rep in range(a.reps + 2):
         for label, env in variants:
             for k in keys:
                 os.environ.pop(k, None)
             os.environ.update(env)
             t0 = time.perf_counter()
-            call(bam, gr, opts=opts, **kw)
+            got = call(bam, gr, opts=opts, **kw)
             wall = (time.perf_counter() - t0) * 1e3
+            if rep == 0:                     # every variant must return what the first one returned, bit for bit
+                import numpy as np
+                flat = WL.as_flat(got)
+                if first_result is None:
+                    first_result = flat.copy()
+                elif not np.array_equal(flat, first_result):
+                    raise SystemExit(f"variant {label!r} changes the result")
+            del got
             t = B.timings()
             if rep >= 2:
                 res[label].append(dict(wall=wall, total=t["ms_total"], plan=t["ms_plan"], fetch=t["ms_fetch"],

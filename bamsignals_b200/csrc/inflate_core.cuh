@@ -59,33 +59,47 @@ BSG_HD uint32_t rev_bits(uint32_t code, uint32_t len) {
 // Bit reader over aligned 32-bit words with two words of look-ahead: peek() is one funnel shift, consume() is an
 // add plus a predicated word rotation whose load was issued a word earlier.  Positions are 32-bit word indices into
 // one 4-byte aligned buffer (the batch's compressed bytes), so the state is five 32-bit registers.
-struct BitReader {
+// kPrefetch (device only, EXPERIMENT for round 2, never on in production): the two words of look-ahead hide an L1 hit
+// but not the one refill in 32 that opens a new 128-byte line of compressed input (ncu: ~14 % of the inflate kernel's
+// stall samples sit on the refill, profiles/r1b_k_inflate_hot_lines.md); 1 / 2 = prefetch the NEXT line into L1 / L2
+// whenever the reader enters a line.
+template <int kPrefetch>
+struct BitReaderT {
     const uint32_t* base;  // the buffer (uniform for all blocks of a launch)
     uint32_t wi;           // index of the next word to load
     uint32_t w0, w1, w2, bo;
+    BSG_HD void prefetch_next_line() const {
+#if defined(__CUDA_ARCH__)
+        if (kPrefetch == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 32u));
+        if (kPrefetch == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + 32u));
+#endif
+    }
     BSG_HD void init(const uint32_t* buf, uint32_t byte_off) {
         base = buf;
         wi = byte_off >> 2;
         bo = (byte_off & 3u) * 8u;
         w0 = base[wi]; w1 = base[wi + 1]; w2 = base[wi + 2];
         wi += 3;
+        if (kPrefetch) prefetch_next_line();
     }
     BSG_HD uint32_t peek() const { return funnel_r(w0, w1, bo); }           // next 32 bits
     BSG_HD uint32_t peek_hi() const { return funnel_r(w1, w2, bo); }        // the 32 bits after those
     BSG_HD void consume_short(uint32_t n) {                                   // n <= 32
         bo += n;
-        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
+        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line(); }
     }
     BSG_HD void consume(uint32_t n) {                                         // n <= 64
         bo += n;
         if (bo >= 32) {
             bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++];
-            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
+            if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line();
+            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line(); }
         }
     }
     BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 32u + bo; }  // bits from the start of the buffer
     BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 4u + (bo >> 3); }   // only valid when bo is a multiple of 8
 };
+using BitReader = BitReaderT<0>;
 
 struct Tables {
     uint16_t lit[1 << kLitBits];
@@ -205,7 +219,8 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint16_t* primary, int bits,
 // Block header: reads BFINAL/BTYPE and, for Huffman blocks, the code lengths, then builds the tables.
 // `lens` is kLensBytes of scratch (the kernel lends the empty token queue).
 // Returns 0 = Huffman block ready, 1 = stored block (caller handles LEN/NLEN), 2 = error.
-BSG_HD int read_block_header(BitReader& br, Tables& T, uint8_t* lens, int* last) {
+template <class BR>
+BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* lens, int* last) {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     uint32_t v = br.peek();
     *last = int(v & 1u);
@@ -271,8 +286,8 @@ BSG_HD int read_block_header(BitReader& br, Tables& T, uint8_t* lens, int* last)
 // sticky (errors do not stop the loop: every access stays in bounds, the caller discards the round).
 // A match is decoded from ONE 64-bit look-ahead (length code + extra bits <= 20 bits, distance code + extra bits
 // <= 28 bits) and consumed once.
-template <class A>
-BSG_HD int fill_queue(BitReader& br, const A& acc, uint32_t* op_dec, int* eob, int* bad) {
+template <class BR, class A>
+BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad) {
     constexpr uint32_t kLitMask2 = ((1u << kLitBits) - 1u) << 1, kDistMask2 = ((1u << kDistBits) - 1u) << 1;
     uint32_t qo = 0;                  // byte offset of the next queue slot
     uint32_t op = *op_dec;

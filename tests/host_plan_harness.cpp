@@ -37,6 +37,11 @@ int main(int argc, char** argv) {
             const int32_t wids[4] = {L, 1000, 5000, 300};
             for (int k = 0; k < 4; ++k) { seq_idx.push_back(int32_t(t)); loc.push_back(locs[k]); width.push_back(wids[k]); strand.push_back(int8_t(k % 3 - 1)); }
         }
+        {   // the entry points must come out strictly ascending whichever sort produced them
+            const auto& ent = bam.entry_points();
+            for (size_t i = 1; i < ent.size(); ++i)
+                if (ent[i - 1] >= ent[i]) fail(BSG_EARG, "internal error: index entry points are not sorted and unique");
+        }
         Regions rg;
         resolve_regions(bam, int64_t(loc.size()), levels.data(), int32_t(levels.size()), seq_idx.data(), loc.data(), width.data(),
                         strand.data(), &rg);
@@ -60,7 +65,7 @@ int main(int argc, char** argv) {
         }
         // the helpers the multi-device sharding uses
         for (size_t t = 0; t < names.size() && t < 64; ++t) { (void)bam.bp_per_block(int(t)); (void)bam.approx_coffset(int(t), lens[t] / 2); }
-        printf("ok refs %zu segments %zu inflated %lld records %lld\n", names.size(), segs.size(), ub, n_rec);
+        printf("ok refs %zu segments %zu inflated %lld records %lld entries %zu\n", names.size(), segs.size(), ub, n_rec, bam.entry_points().size());
     } catch (Error& e) {
         printf("error %d %s\n", e.code, e.msg.c_str());
     } catch (std::bad_alloc&) {

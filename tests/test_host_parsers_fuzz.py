@@ -78,6 +78,19 @@ def test_valid_seeds_plan_everything(harness, seeds, tmp_path):
         assert out.startswith("ok refs 3 ") and " records 800" in out, out      # 2 x 400 placed reads; the 17 unplaced ones are never fetched
 
 
+def test_large_index_takes_the_radix_sort(harness, tmp_path):
+    """An index with more than 16 Ki entry points (the radix-sort path of load_index): whole-contig plans must still
+    reach every placed record, and the harness checks that the entry points are strictly ascending."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import workloads as WL
+    bam, info = WL.make_bam("c2", 0.03, str(tmp_path))
+    out = run(harness, bam, ext=0)
+    f = out.split()
+    assert f[0] == "ok" and int(f[f.index("records") + 1]) == info["records"], out
+    assert int(f[f.index("entries") + 1]) > (1 << 14), out
+
+
 @pytest.mark.parametrize("which", ["bai", "csi"])
 def test_mutated_index(harness, seeds, tmp_path, which):
     bam, suf, idx = seeds[0 if which == "bai" else 1]

@@ -147,10 +147,10 @@ def run_ours(args, rank, world, local_rank):
             ksum[k] += t[k]
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
-    clocks = sampler.summary()
     reads = t["records"]
     st.close()
     if args.profile:                     # ncu runs: only the resident steps matter
+        sampler.summary()                # stops the nvidia-smi child
         if rank == 0:
             print(json.dumps({"profile_only": True, "ms_device_per_step": dev_ms / args.steps, "kernels_ms": ksum,
                               "launches": launches, "reads_decoded": reads}), flush=True)
@@ -168,6 +168,9 @@ def run_ours(args, rank, world, local_rank):
         te = B.timings()
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
+    # clocks + throttle reasons sampled over BOTH timed regions (the resident steps alone last a few milliseconds, less
+    # than one 100 ms nvidia-smi sample)
+    clocks = sampler.summary()
     if gpu_inflate > 0:     # compressed bytes + block descriptors (16 B + 4 B CRC per <= 64 KiB block) + tiles
         h2d = te["bytes_compressed"] + 20 * (te["bytes_inflated"] // 65280 + 1) + 24 * te["n_tiles"]
     else:                   # inflated bytes + record offsets + tiles

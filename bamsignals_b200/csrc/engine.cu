@@ -319,6 +319,27 @@ public:
             }
             batches_.push_back(std::move(b));
         }
+        // EXPERIMENT (BSG_SHORT_LAST=1, unmeasured, off by default): whatever the last batch finalises is counted, copied
+        // and scattered behind the last inflate with nothing left to overlap it; a last batch of a quarter of the usual
+        // size leaves only its small share of the result there (the mirror image of the short first batch).
+        if (gpu && !keep_raw && opts_.batch_bytes <= 0 && getenv("BSG_SHORT_LAST") && !batches_.empty()) {
+            Batch* L = batches_.back().get();
+            const uint64_t want = uint64_t(batch_bytes) / 4;
+            if (L->bytes > 2 * want && L->seg_last - L->seg_first >= 2) {
+                uint64_t tail = 0;
+                size_t k = L->seg_last;
+                while (k > L->seg_first + 1 && tail + ((segs_[k - 1].usize + 15) & ~15ull) <= want) {
+                    tail += (segs_[k - 1].usize + 15) & ~15ull;
+                    --k;
+                }
+                if (k < L->seg_last) {
+                    auto nb = std::make_unique<Batch>();
+                    nb->seg_first = k; nb->seg_last = L->seg_last; nb->bytes = tail;
+                    L->seg_last = k; L->bytes -= tail;
+                    batches_.push_back(std::move(nb));
+                }
+            }
+        }
         rows_cap_ = (rows_cap + 3) & ~int64_t(3);
         tm_.bytes_compressed = int64_t(total_c);
         tm_.bytes_inflated = int64_t(total_bytes);

@@ -24,6 +24,9 @@ timeout 900 python tools/e2e_ab.py --preset c4 --gscale 0.1 --reps 7 s2: s4:BSG_
     v1:BSG_INFLATE_VARIANT=1 v2:BSG_INFLATE_VARIANT=2 v4:BSG_INFLATE_VARIANT=4 v5:BSG_INFLATE_VARIANT=5 v6:BSG_INFLATE_VARIANT=6 \
     > $O/r2_ab_inflate_c4_g0.1.json 2>> $O/r2_ab.err
 cat $O/r2_ab_inflate_c2.json $O/r2_ab_inflate_c4_g0.1.json
+# host-side experiment: a short LAST batch (engine.cu, BSG_SHORT_LAST=1) to shrink the count/copy/scatter tail of a call
+timeout 600 python tools/e2e_ab.py --preset c2 --reps 9 base: short_last:BSG_SHORT_LAST=1 > $O/r2_ab_short_last_c2.json 2>> $O/r2_ab.err
+cat $O/r2_ab_short_last_c2.json
 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > $O/r2_racecheck.log 2>&1
 echo "racecheck rc=$?" >> $O/r2_racecheck.log
 tail -5 $O/r2_racecheck.log

@@ -1,10 +1,14 @@
-// Minimal stand-in for <Rcpp.h>: just the types and members rshim/bamsignals_shim.cpp uses, with the signatures of
-// the real ones (Rcpp 1.0.x: Vector<INTSXP>, Matrix<INTSXP>, Vector<STRSXP>, Vector<VECSXP>, RObject, as<>, stop).
+// Minimal stand-in for <Rcpp.h>: just the types and members rshim/bamsignals_shim.cpp AND the reference's own
+// src/bamsignals.cpp use (the latter is compiled UNCHANGED against this header into oracle/_ref/, see oracle/Makefile),
+// with the signatures of the real ones (Rcpp 1.0.x: Vector<INTSXP>, Matrix<INTSXP>, Vector<STRSXP>, Vector<VECSXP>,
+// RObject, String, as<>, stop).
 // TEST INFRASTRUCTURE: R and Rcpp cannot be installed offline, so tests/test_rshim_compiles.py compiles the shim
 // against this header to check its C++ and, above all, every call into include/bamsignals_cuda.h (argument count,
 // order and types).  The mock is functional enough to RUN the shim on plain C++ objects (see rshim_mock_driver.cpp).
 #pragma once
+#include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -62,9 +66,12 @@ class IntegerVector : public RObject {
 public:
     typedef int* iterator;
     IntegerVector() {}
-    explicit IntegerVector(R_xlen_t n) { p_->ints.assign(size_t(n), 0); }
+    // (two ints of slack capacity: the reference's Coverager::pileup increments array[0] of a zero-width region's EMPTY
+    // vector, src/bamsignals.cpp:420-424 - in R that write lands behind the object's header; here it lands in the slack)
+    explicit IntegerVector(R_xlen_t n) { p_->ints.reserve(size_t(n) + 2); p_->ints.assign(size_t(n), 0); }
     IntegerVector(SEXP p) : RObject(std::move(p)) {}
     R_xlen_t size() const { return R_xlen_t(p_->ints.size()); }
+    R_xlen_t length() const { return size(); }
     int& operator[](R_xlen_t i) { return p_->ints[size_t(i)]; }
     const int& operator[](R_xlen_t i) const { return p_->ints[size_t(i)]; }
     iterator begin() { return p_->ints.data(); }
@@ -73,7 +80,7 @@ public:
 class IntegerMatrix : public RObject {
 public:
     typedef int* iterator;
-    IntegerMatrix(int nrow, R_xlen_t ncol) { p_->ints.assign(size_t(nrow) * size_t(ncol), 0); p_->nrow = nrow; }
+    IntegerMatrix(int nrow, R_xlen_t ncol) { p_->ints.reserve(size_t(nrow) * size_t(ncol) + 2); p_->ints.assign(size_t(nrow) * size_t(ncol), 0); p_->nrow = nrow; }
     iterator begin() { return p_->ints.data(); }
 };
 
@@ -86,11 +93,24 @@ private:
     std::string* s_;
 };
 
+// Rcpp::String: what indexing a CharacterVector yields once it leaves the vector (src/bamsignals.cpp:86-88,116-125)
+class String {
+public:
+    String() {}
+    String(const StringProxy& p) : s_(p.get()) {}
+    String(std::string s) : s_(std::move(s)) {}
+    operator std::string() const { return s_; }
+    const char* get_cstring() const { return s_.c_str(); }
+private:
+    std::string s_;
+};
+
 class CharacterVector : public RObject {
 public:
     CharacterVector() {}
     CharacterVector(SEXP p) : RObject(std::move(p)) {}
     R_xlen_t size() const { return R_xlen_t(p_->strs.size()); }
+    R_xlen_t length() const { return size(); }
     StringProxy operator[](R_xlen_t i) const { return StringProxy(&p_->strs[size_t(i)]); }
     static CharacterVector create(const char* a, const char* b) { CharacterVector v; v.p_->strs = {a, b}; return v; }
 };
@@ -107,7 +127,9 @@ private:
 class List : public RObject {
 public:
     explicit List(R_xlen_t n) { p_->items.assign(size_t(n), SEXP()); }
+    List(SEXP p) : RObject(std::move(p)) {}
     R_xlen_t size() const { return R_xlen_t(p_->items.size()); }
+    R_xlen_t length() const { return size(); }
     ItemProxy operator[](R_xlen_t i) { return ItemProxy(&p_->items[size_t(i)]); }
 };
 

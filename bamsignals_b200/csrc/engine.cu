@@ -15,8 +15,11 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "bamio.h"
 #include "common.h"
@@ -78,7 +81,8 @@ struct DeviceCtx {
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
     DevBuf tab[2], c0, c1, tiles_i32, tiles_i64, out, scalars;
-    DevBuf raw_all, offs_all, batch_table;      // resident raw bytes of a staged session
+    uint64_t tiles_gen = 0;                     // bumped whenever a Session uploads tiles: a staged Session's cached tiles are
+                                                // only valid while no other call has replaced them on this device
     DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
     PinBuf h_total;
     cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
@@ -138,7 +142,7 @@ struct DeviceCtx {
         }
         for (auto& b : tab) b.release();
         c0.release(); c1.release(); tiles_i32.release(); tiles_i64.release(); out.release(); scalars.release();
-        raw_all.release(); offs_all.release(); batch_table.release(); h_scalars.release();
+        h_scalars.release();
         for (int i = 0; i < kOutSlots; ++i) { h_out[i].release(); cudaEventDestroy(ev_d2h[i]); }
         h_tiles.release(); h_front.release();
         cudaEventDestroy(ev_front[0]); cudaEventDestroy(ev_front[1]);
@@ -190,6 +194,28 @@ Pool& get_pool(int want) {
     return *g_pool;
 }
 
+// The caller's options, whatever version of the struct it was compiled against: the first struct_size bytes are taken,
+// the rest are defaults (all zero).  verify_crc: 0 = default = on, -1 = off.
+bsg_opts effective_opts(const bsg_opts* opts) {
+    bsg_opts o;
+    memset(&o, 0, sizeof o);
+    if (opts) {
+        if (opts->struct_size < int32_t(sizeof(int32_t)) || opts->struct_size > (1 << 16))
+            fail(BSG_EARG, "bsg_opts.struct_size must be set to sizeof(bsg_opts)");
+        memcpy(&o, opts, std::min<size_t>(size_t(opts->struct_size), sizeof o));
+    }
+    o.struct_size = int32_t(sizeof o);
+    o.verify_crc = o.verify_crc < 0 ? 0 : 1;
+    return o;
+}
+
+// NVTX range of one pipeline stage on the calling thread (header-only nvtx3: a no-op unless a profiler is attached)
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx&) = delete;
+};
+
 struct Span { cudaEvent_t a, b; };
 struct KernelTimes {
     std::vector<Span> decode, filter, join, count, all;
@@ -225,10 +251,7 @@ class Session {
 public:
     Session(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
             const int32_t* loc, const int32_t* width, const int8_t* strand, const bsg_opts* opts)
-        : bamp_(open_bam(bampath)), bam_(*bamp_) {
-        if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) opts_ = *opts;
-        else { memset(&opts_, 0, sizeof opts_); opts_.verify_crc = 1; }
-        if (const char* e = getenv("BSG_BATCH_MB")) opts_.batch_bytes = int64_t(atoll(e)) << 20;   // experiment switch
+        : bamp_(open_bam(bampath)), bam_(*bamp_), opts_(effective_opts(opts)) {
         resolve_regions(bam_, R, seq_levels, n_levels, seq_idx, loc, width, strand, &rg_);
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -268,6 +291,7 @@ public:
         plan_ext_ = ext;
         plan_thread_ = std::thread([this, ext] {
             const double t0 = now_ms();
+            Nvtx r("bsg:plan_fetch");
             try { plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_); }
             catch (Error& e) { plan_err_ = e; }
             catch (std::exception& e) { plan_err_ = Error{BSG_EARG, std::string("internal error: ") + e.what()}; }
@@ -302,7 +326,7 @@ public:
             // (Measured: batches well below 1 GiB leave the inflate kernel with fewer BGZF blocks than the 148 x 56
             // streams the GPU holds - a 128 MiB ... 1 GiB ramp cost C2 30 ms end to end.)  Only the FIRST batch is
             // short: nothing overlaps its upload, so the device starts after a quarter of the usual copy.
-            const bool first_short = gpu && !keep_raw && opts_.batch_bytes <= 0 && i == 0 && !getenv("BSG_NO_SHORT_FIRST");
+            const bool first_short = gpu && !keep_raw && opts_.batch_bytes <= 0 && i == 0;
             const uint64_t limit = first_short ? uint64_t(batch_bytes) / 4 : uint64_t(batch_bytes);
             uint64_t acc = 0;
             while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= limit)) {
@@ -318,27 +342,6 @@ public:
                 total_bytes += segs_[k].usize; total_c += segs_[k].csize;
             }
             batches_.push_back(std::move(b));
-        }
-        // EXPERIMENT (BSG_SHORT_LAST=1, unmeasured, off by default): whatever the last batch finalises is counted, copied
-        // and scattered behind the last inflate with nothing left to overlap it; a last batch of a quarter of the usual
-        // size leaves only its small share of the result there (the mirror image of the short first batch).
-        if (gpu && !keep_raw && opts_.batch_bytes <= 0 && getenv("BSG_SHORT_LAST") && !batches_.empty()) {
-            Batch* L = batches_.back().get();
-            const uint64_t want = uint64_t(batch_bytes) / 4;
-            if (L->bytes > 2 * want && L->seg_last - L->seg_first >= 2) {
-                uint64_t tail = 0;
-                size_t k = L->seg_last;
-                while (k > L->seg_first + 1 && tail + ((segs_[k - 1].usize + 15) & ~15ull) <= want) {
-                    tail += (segs_[k - 1].usize + 15) & ~15ull;
-                    --k;
-                }
-                if (k < L->seg_last) {
-                    auto nb = std::make_unique<Batch>();
-                    nb->seg_first = k; nb->seg_last = L->seg_last; nb->bytes = tail;
-                    L->seg_last = k; L->bytes -= tail;
-                    batches_.push_back(std::move(nb));
-                }
-            }
         }
         rows_cap_ = (rows_cap + 3) & ~int64_t(3);
         tm_.bytes_compressed = int64_t(total_c);
@@ -357,10 +360,10 @@ public:
         if (keep_raw) {
             size_t tot = 0;
             for (auto& b : batches_) tot += (b->bytes + 64 + 255) & ~255ull;
-            c.raw_all.ensure(tot + 64);
+            raw_all_.ensure(tot + 64);
             size_t offs_tot = size_t(rows_cap_) + batches_.size() + 8;
             if (gpu) { offs_tot = 8; for (auto& b : batches_) offs_tot += size_t(b->bytes / kMinRecord) + 2; }
-            c.offs_all.ensure(offs_tot * sizeof(uint32_t));
+            offs_all_.ensure(offs_tot * sizeof(uint32_t));
         }
         ensure_table(rows_cap_);
         c.scalars.ensure(sizeof(DeviceScalars));
@@ -398,7 +401,7 @@ public:
         if (resident_.empty()) return;
         Span sp{c.timing_event(), c.timing_event()};
         BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-        launch_decode_table(c.batch_table.as<DecodeBatch>(), int(resident_.size()), resident_chunks_, table(),
+        launch_decode_table(batch_table_.as<DecodeBatch>(), int(resident_.size()), resident_chunks_, table(),
                             mode == MODE_COVERAGE, fp, c.scalars.as<DeviceScalars>(), c.s_comp);
         BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
         kt_.decode.push_back(sp); kt_.launches += 1;
@@ -434,17 +437,41 @@ public:
         std::unique_lock<std::mutex> lk(pf_m_);
         pf_cv_.wait(lk, [&] { return pf_left_ == 0; });
     }
-    ~Session() { if (plan_thread_.joinable()) plan_thread_.join(); stop_streamer(true); wait_prefault(); }
+    ~Session() {
+        if (plan_thread_.joinable()) plan_thread_.join();
+        stop_streamer(true);
+        wait_prefault();
+        if (raw_all_.p || offs_all_.p || batch_table_.p) {
+            cudaSetDevice(ctx_->dev);
+            cudaDeviceSynchronize();
+            raw_all_.release(); offs_all_.release(); batch_table_.release();
+        }
+    }
 
     // Tiles depend only on the regions and on (mode, binsize, ss, layout): build + upload them before any device
     // work of the call is queued, and keep them for the next call of a staged session.
     void prepare_tiles(Mode mode, int32_t binsize, int ss, const int64_t* out_offsets) {
+        Nvtx r("bsg:tiles");
         DeviceCtx& c = *ctx_;
         const int64_t R = rg_.R;
         if (!out_offsets) fail(BSG_EARG, "out_offsets is required");
-        if (tiles_valid_ && tiles_mode_ == mode && tiles_binsize_ == binsize && tiles_ss_ == ss &&
+        if (tiles_valid_ && my_tiles_gen_ == c.tiles_gen && tiles_mode_ == mode && tiles_binsize_ == binsize && tiles_ss_ == ss &&
             tiles_offsets_.size() == size_t(R + 1) && memcmp(tiles_offsets_.data(), out_offsets, size_t(R + 1) * 8) == 0)
             return;
+        // the layout must be the one allocateList gives (src/bamsignals.cpp:139-192): the host scatter trusts it
+        {
+            const int64_t mult = ss ? 2 : 1;
+            if (R > 0 && out_offsets[0] < 0) fail(BSG_EARG, "out_offsets must not be negative");
+            for (int64_t i = 0; i < R; ++i) {
+                const int64_t want = mode == MODE_COUNT ? mult
+                                   : (mode == MODE_COVERAGE ? int64_t(rg_.width[i])
+                                                            : mult * ((int64_t(rg_.width[i]) + binsize - 1) / binsize));
+                if (out_offsets[i + 1] - out_offsets[i] != want)
+                    fail(BSG_EARG, "out_offsets[" + std::to_string(i + 1) + "] - out_offsets[" + std::to_string(i) + "] is " +
+                                   std::to_string(out_offsets[i + 1] - out_offsets[i]) + ", the layout of this call needs " + std::to_string(want) +
+                                   " (see bsg_output_layout)");
+            }
+        }
         HostTiles& ht = ht_;
         ht = HostTiles();
         // Tile size: as large as shared memory allows (fewer halo re-reads), but small enough that the launch has
@@ -472,6 +499,7 @@ public:
             BSG_CUDA(cudaMemcpyAsync(tl, h + nt * 16, nt * 8, cudaMemcpyHostToDevice, c.s_comp));
             BSG_CUDA(cudaStreamSynchronize(c.s_comp));   // h_tiles is reused by the next call
         }
+        my_tiles_gen_ = ++c.tiles_gen;
         n_tiles_ = nt;
         max_tile_ints_ = ht.max_tile_ints;
         tiles_mode_ = mode; tiles_binsize_ = binsize; tiles_ss_ = ss;
@@ -523,6 +551,7 @@ public:
     }
 
     void finish_count() {
+        Nvtx r("bsg:finish_count+d2h");
         DeviceCtx& c = *ctx_;
         cnt_.rows_ready = n_rows_;
         if (n_tiles_ > cnt_.t_done) count_tiles(cnt_.t_done, n_tiles_);
@@ -568,6 +597,7 @@ private:
 
     // K3 + K4/K5 for tiles [t0, t1) over the rows decoded so far, then hand them to the output streamer
     void count_tiles(int64_t t0, int64_t t1) {
+        Nvtx r("bsg:join+count");
         DeviceCtx& c = *ctx_;
         cudaStream_t st = cnt_stream();
         const int64_t nt_all = n_tiles_, n = t1 - t0;
@@ -618,6 +648,7 @@ private:
         DeviceCtx& c = *ctx_;
         cudaSetDevice(c.dev);
         const int64_t cap = kD2HChunk / 4;
+        nvtxNameOsThreadA(uint32_t(syscall(SYS_gettid)), "bsg result streamer");
         for (;;) {
             OutJob job;
             {
@@ -835,8 +866,8 @@ private:
             const double t0 = now_ms();
             uint8_t* d_raw; uint32_t* d_offs;
             if (keep_raw_) {
-                d_raw = c.raw_all.as<uint8_t>() + raw_base;
-                d_offs = c.offs_all.as<uint32_t>() + offs_base;
+                d_raw = raw_all_.as<uint8_t>() + raw_base;
+                d_offs = offs_all_.as<uint32_t>() + offs_base;
                 resident_.push_back(ResidentBatch{raw_base, offs_base, n});
                 raw_base += (b->bytes + 64 + 255) & ~255ull;
                 offs_base += n + 1;
@@ -945,6 +976,7 @@ private:
             const int slot = int(bi & 1);
             // ---- descriptors -----------------------------------------------------------------------------------------
             double tt = now_ms();
+            nvtxRangePushA("bsg:batch descriptors");
             blocks.clear(); crcs.clear(); walkers.clear(); pieces.clear();
             uint64_t ubase = 0, cbase = 0;
             for (size_t k = b->seg_first; k < b->seg_last; ++k) {
@@ -974,6 +1006,7 @@ private:
                 cbase += (fend - fbeg + 15) & ~15ull;
             }
             const uint32_t end_pos = walkers.empty() ? 0u : walkers.back().y;
+            nvtxRangePop();
             t_desc += now_ms() - tt; tt = now_ms();
             // ---- buffers ------------------------------------------------------------------------------------------------
             // The upload overwrites only the compressed bytes and the descriptor arrays of this slot; their readers are
@@ -983,6 +1016,7 @@ private:
             BSG_CUDA(cudaEventSynchronize(c.ev_total[slot]));
             BSG_CUDA(cudaEventSynchronize(c.ev_crc[slot]));
             t_wait += now_ms() - tt; tt = now_ms();
+            nvtxRangePushA("bsg:upload compressed (memcpy + H2D)");
             c.g_comp[slot].ensure(cbase + 4096);   // slack: the bit reader looks ahead, and a corrupt stream may run on for one round
             c.g_blocks[slot].ensure(blocks.size() * sizeof(InflateBlock) + 64);
             c.g_crc[slot].ensure(crcs.size() * 4 + 64);
@@ -991,8 +1025,8 @@ private:
             c.g_base[slot].ensure(walkers.size() * 4 + 64);
             uint8_t* d_raw; uint32_t* d_offs;
             if (keep_raw_) {
-                d_raw = c.raw_all.as<uint8_t>() + raw_base;
-                d_offs = c.offs_all.as<uint32_t>() + offs_base;
+                d_raw = raw_all_.as<uint8_t>() + raw_base;
+                d_offs = offs_all_.as<uint32_t>() + offs_base;
             } else {
                 c.g_raw[slot].ensure(max_batch + 64);
                 c.g_offs[slot].ensure((max_offs + 8) * sizeof(uint32_t));
@@ -1043,7 +1077,9 @@ private:
             if (!walkers.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, walkers.data(), walkers.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.s_copy));
             BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
             BSG_CUDA(cudaStreamSynchronize(c.s_copy));                 // blocks/walkers vectors are reused next iteration
+            nvtxRangePop();
             t_copy += now_ms() - tt; tt = now_ms();
+            nvtxRangePushA("bsg:launch inflate + crc + walk");
             // ---- device: inflate -> walk -> total ------------------------------------------------------------------------------
             BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
             BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_gfree[slot], 0));       // decode (+ CRC) of the slot's previous batch
@@ -1077,9 +1113,12 @@ private:
             kt_.launches += (blocks.empty() ? 0 : 1) + (walkers.empty() ? 1 : 3);
             BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ws));
             BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));
+            nvtxRangePop();
             // ---- previous batch: decode ------------------------------------------------------------------------------------------
             tt = now_ms();
+            nvtxRangePushA("bsg:decode previous batch + stream out");
             finish(pend);
+            nvtxRangePop();
             t_finish += now_ms() - tt;
             pend.valid = true; pend.slot = slot; pend.d_raw = d_raw; pend.d_offs = d_offs; pend.raw_base = raw_base; pend.offs_base = offs_base;
             if (keep_raw_) {
@@ -1109,15 +1148,15 @@ private:
         int64_t row0 = 0;
         for (auto& rb : resident_) {
             if (rb.n > 0) {
-                tab.push_back(DecodeBatch{c.raw_all.as<uint8_t>() + rb.raw_base, c.offs_all.as<uint32_t>() + rb.offs_base, row0, int32_t(rb.n), chunks});
+                tab.push_back(DecodeBatch{raw_all_.as<uint8_t>() + rb.raw_base, offs_all_.as<uint32_t>() + rb.offs_base, row0, int32_t(rb.n), chunks});
                 chunks += int((rb.n + kDecodeChunk - 1) / kDecodeChunk);
             }
             row0 += rb.n;
         }
         resident_.resize(tab.size());
         resident_chunks_ = chunks;
-        c.batch_table.ensure(tab.size() * sizeof(DecodeBatch) + 64);
-        if (!tab.empty()) BSG_CUDA(cudaMemcpy(c.batch_table.p, tab.data(), tab.size() * sizeof(DecodeBatch), cudaMemcpyHostToDevice));
+        batch_table_.ensure(tab.size() * sizeof(DecodeBatch) + 64);
+        if (!tab.empty()) BSG_CUDA(cudaMemcpy(batch_table_.p, tab.data(), tab.size() * sizeof(DecodeBatch), cudaMemcpyHostToDevice));
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
     }
 
@@ -1132,6 +1171,8 @@ private:
     std::vector<Segment> segs_;
     std::vector<std::unique_ptr<Batch>> batches_;
     std::vector<ResidentBatch> resident_;
+    DevBuf raw_all_, offs_all_, batch_table_;   // a staged session OWNS its resident raw bytes, offsets and batch table
+    uint64_t my_tiles_gen_ = 0;
     int64_t rows_cap_ = 0, n_rows_ = 0;
     bool keep_raw_ = false;
     int64_t staged_ext_ = 0;
@@ -1191,13 +1232,6 @@ int64_t ext_pileup(const int32_t* tlen_filter, int32_t shift, int32_t pe_mid) {
 int64_t ext_coverage(const int32_t* tlen_filter, int32_t tspan) {
     if (tspan && !tlen_filter) fail(BSG_EARG, "tspan requires a tlen_filter");
     return tspan ? int64_t(tlen_filter[1]) : 0;                                       // src/bamsignals.cpp:487
-}
-
-bsg_opts effective_opts(const bsg_opts* opts) {
-    bsg_opts o;
-    if (opts && opts->struct_size >= int32_t(sizeof(bsg_opts))) o = *opts;
-    else { memset(&o, 0, sizeof o); o.verify_crc = 1; }
-    return o;
 }
 
 // A call on several devices: the regions are cut into contiguous shards in (chromosome, start) order, balanced by
@@ -1331,6 +1365,12 @@ struct bsg_stage {
     std::unique_ptr<Session> s;
 };
 
+namespace {
+// open staged sessions: bsg_shutdown() ends them (their device memory and streams are about to go away); the handles stay
+// valid to pass to bsg_stage_close(), every other use is refused
+std::vector<bsg_stage*> g_stages;
+}
+
 extern "C" {
 
 int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels, const int32_t* seq_idx,
@@ -1418,6 +1458,7 @@ int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* c
         h->s.reset(new Session(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts));
         h->s->stage(ext_hint, true);
         h->s->finish_timings(t0);
+        g_stages.push_back(h.get());
         *st = h.release();
     });
 }
@@ -1425,8 +1466,9 @@ int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* c
 int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t binsize, int32_t shift,
                       int32_t ss, int32_t requiredF, int32_t filteredF, int32_t pe_mid, int32_t* out,
                       const int64_t* out_offsets) {
-    if (!st || !st->s) { g_err = "null stage"; return BSG_EARG; }
+    if (!st) { g_err = "null stage"; return BSG_EARG; }
     return guarded([&] {
+        if (!st->s) fail(BSG_EARG, "this staged session was ended by bsg_shutdown()");
         const double t0 = now_ms();
         st->s->reset_counters();
         st->s->require_ext(ext_pileup(tlen_filter, shift, pe_mid));
@@ -1440,8 +1482,9 @@ int bsg_pileup_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual
 
 int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqual, int32_t requiredF,
                         int32_t filteredF, int32_t tspan, int32_t* out, const int64_t* out_offsets) {
-    if (!st || !st->s) { g_err = "null stage"; return BSG_EARG; }
+    if (!st) { g_err = "null stage"; return BSG_EARG; }
     return guarded([&] {
+        if (!st->s) fail(BSG_EARG, "this staged session was ended by bsg_shutdown()");
         const double t0 = now_ms();
         st->s->reset_counters();
         st->s->require_ext(ext_coverage(tlen_filter, tspan));
@@ -1456,7 +1499,8 @@ int bsg_coverage_staged(bsg_stage* st, const int32_t* tlen_filter, int32_t mapqu
 void bsg_stage_close(bsg_stage* st) {
     if (!st) return;
     std::lock_guard<std::mutex> g(g_mu);
-    delete st;
+    g_stages.erase(std::remove(g_stages.begin(), g_stages.end(), st), g_stages.end());
+    delete st;                                   // returns the session's resident device memory
 }
 
 const char* bsg_last_error(void) { return g_err.c_str(); }
@@ -1475,6 +1519,7 @@ int bsg_device_count(void) {
 
 void bsg_shutdown(void) {
     std::lock_guard<std::mutex> g(g_mu);
+    for (bsg_stage* st : g_stages) st->s.reset();
     for (auto& c : g_ctx) c.release();
     g_pool.reset();
     g_bams.clear();

@@ -16,8 +16,6 @@
 // copies (142-282 ms), one stream per lane (235 ms: ~10 active lanes, 3 warps/SM, latency-bound).  This kernel: 127 ms.
 #include "kernels.cuh"
 
-#include <cstdlib>
-
 #include "inflate_core.cuh"
 
 namespace bsg {
@@ -40,10 +38,9 @@ constexpr int kQ2Warps = 4;
 #ifndef BSG_Q2_MINB
 #define BSG_Q2_MINB 7
 #endif
-// Warps per CTA by streams per warp: the static shared memory of a CTA (warps x streams x 3.7 KB) must stay below 48 KB,
-// and 7 CTAs per SM must keep 56 streams resident either way.  The four-stream instantiation is an EXPERIMENT (round 2:
-// BSG_INFLATE_STREAMS=4): four serial decode chains share phase 1's instructions instead of two, at half the warps.
-template <int kStreams> struct Q2Cfg { static constexpr int kWarps = kStreams == 4 ? 2 : kQ2Warps; };
+// (Round 2, profiles/r2_ab_inflate_variants_*.json: ONE stream per warp 82.8 ms, FOUR streams per warp at half the warps
+// 99.2 ms against 73.7 ms for two - with fewer warps the serialised queues of phase 2 are no longer hidden.)
+constexpr int kStreams = 2;
 struct Q2Smem {
     inflate_core::Tables T;
     uint32_t q[inflate_core::kQueue];
@@ -92,10 +89,8 @@ struct SmemAccess {
 };
 
 // Phase 2: all 32 lanes materialise one stream's token queue q[0..nq) behind out[pos_base); returns the new pos_base.
-// kLoadsFirst (EXPERIMENT for round 2, off in production): a short match that does not overlap itself (dist >= len)
-// issues the loads of ALL its source words before its first store, instead of one dependent L2 round trip per
-// 8-byte piece (ncu: 10.5 % of the kernel's stall samples wait on those loads, profiles/r1b_k_inflate_hot_lines.md).
-template <bool kLoadsFirst>
+// (Round 2: issuing all loads of a non-overlapping short match before its first store was measured at 73.1 vs 73.7 ms -
+// no gain, dropped.)
 __device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int nq, uint8_t* out, uint32_t pos_base, int lane) {
     using namespace inflate_core;
     for (int base = 0; base < nq; base += 32) {
@@ -143,29 +138,7 @@ __device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int 
                 continue;
             }
             const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
-            if (kLoadsFirst && ready && own_dist >= own_len) {
-                // own_len <= 32: at most nine aligned words cover the source; the bytes they hold around it are finished
-                // output of this or the previous block, or this round's bytes of other lanes that nobody looks at
-                const uint8_t* sp = out + pos - own_dist;
-                const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-                const uint32_t sh = uint32_t(sa & 3u) * 8u;
-                const uint32_t nwords = (uint32_t(sa & 3u) + own_len + 3u) >> 2;
-                uint32_t a[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) a[k] = uint32_t(k) < nwords ? wp[k] : 0u;
-                uint8_t* d = out + pos;
-#pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    if (uint32_t(8 * pc) < own_len) {
-                        const uint32_t lo = __funnelshift_r(a[2 * pc], a[2 * pc + 1], sh), hi = __funnelshift_r(a[2 * pc + 1], a[2 * pc + 2], sh);
-                        const uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
-                        const uint32_t n = min(own_len - uint32_t(8 * pc), 8u);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[8 * pc + k] = uint8_t(w >> (8 * k));
-                    }
-                }
-            } else if (ready) {
+            if (ready) {
                 for (uint32_t done = 0; done < own_len; done += 8u) {
                     const uint32_t n = min(own_len - done, 8u);
                     uint8_t* d = out + pos + done;
@@ -199,19 +172,15 @@ __device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int 
     return pos_base;
 }
 
-// kVariant (EXPERIMENTS for round 2; 0 = production): bits 0-1 = compressed-input prefetch of the bit reader (1 = into
-// L1, 2 = into L2), bit 2 = loads-first copies of short non-overlapping matches.  BSG_INFLATE_VARIANT selects one.
-template <int kStreams, int kVariant>
-__global__ void __launch_bounds__(Q2Cfg<kStreams>::kWarps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
-                                                                  const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
+__global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
+                                                                        const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
-    static_assert(kStreams == 1 || kStreams == 2 || kStreams == 4, "one, two or four streams per warp");
-    constexpr int kWarps = Q2Cfg<kStreams>::kWarps;
+    constexpr int kWarps = kQ2Warps;
     constexpr int kLanes = 32 / kStreams;                    // lanes per stream in phase 1; the first of them decodes
     __shared__ Q2Smem s_mem[kWarps][kStreams];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = kStreams > 1 ? lane / kLanes : 0;        // the stream this lane belongs to in phase 1
-    const bool dec = kStreams > 1 ? (lane & (kLanes - 1)) == 0 : lane == 0;      // lanes 0 (and 16; or 0, 8, 16, 24) decode
+    const int sub = lane / kLanes;                           // the stream this lane belongs to in phase 1
+    const bool dec = (lane & (kLanes - 1)) == 0;             // lanes 0 and 16 decode
     const int b = (blockIdx.x * kWarps + wid) * kStreams + sub;
     if ((blockIdx.x * kWarps + wid) * kStreams >= n_blocks) return;       // whole warp idle
     Tables& T = s_mem[wid][sub].T;
@@ -227,7 +196,7 @@ __global__ void __launch_bounds__(Q2Cfg<kStreams>::kWarps * 32, BSG_Q2_MINB) k_i
     if (!fin) blk = blocks[b];
     uint8_t* out = raw + blk.out_off;
     const uint32_t out_len = blk.out_len;
-    BitReaderT<(kVariant & 3)> br;
+    BitReader br;
     br.base = reinterpret_cast<const uint32_t*>(comp);     // cudaMalloc'ed: aligned
     br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
     if (dec && !fin) br.init(br.base, blk.in_off);
@@ -275,7 +244,7 @@ __global__ void __launch_bounds__(Q2Cfg<kStreams>::kWarps * 32, BSG_Q2_MINB) k_i
             const uint32_t pb_s = __shfl_sync(FULL, pos_base, src);
             const uint32_t oo_s = __shfl_sync(FULL, blk.out_off, src);
             if (st_s >= 2 || nq_s == 0) continue;            // warp-uniform
-            const uint32_t pb_new = materialise<(kVariant & 4) != 0>(s_mem[wid][s].q, nq_s, raw + oo_s, pb_s, lane);
+            const uint32_t pb_new = materialise(s_mem[wid][s].q, nq_s, raw + oo_s, pb_s, lane);
             if (lane == src) pos_base = pb_new;
         }
         __syncwarp();
@@ -432,24 +401,9 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s) {
     if (n_blocks <= 0) return;
-    // BSG_INFLATE_STREAMS=1 / 4 select the one- / four-streams-per-warp instantiations (A/B measurements only; the
-    // four-stream one has not been on a GPU yet); anything else is the production kernel with two streams per warp
-    const int want = getenv("BSG_INFLATE_STREAMS") ? atoi(getenv("BSG_INFLATE_STREAMS")) : 2;
-    const int streams = want == 1 ? 1 : (want == 4 ? 4 : 2);
-    const int warps = streams == 4 ? Q2Cfg<4>::kWarps : kQ2Warps;
-    const int per_cta = warps * streams;
+    const int per_cta = kQ2Warps * kStreams;
     const int grid = (n_blocks + per_cta - 1) / per_cta;
-    // BSG_INFLATE_VARIANT (two streams per warp only): 1 / 2 = prefetch the next line of compressed input into L1 / L2,
-    // 4 = loads-first short-match copies, 5 / 6 = both.  Unmeasured experiments; 0 / unset = production.
-    const int variant = (streams == 2 && getenv("BSG_INFLATE_VARIANT")) ? atoi(getenv("BSG_INFLATE_VARIANT")) : 0;
-    if (streams == 1) k_inflate_q2<1, 0><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (streams == 4) k_inflate_q2<4, 0><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (variant == 1) k_inflate_q2<2, 1><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (variant == 2) k_inflate_q2<2, 2><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (variant == 4) k_inflate_q2<2, 4><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (variant == 5) k_inflate_q2<2, 5><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else if (variant == 6) k_inflate_q2<2, 6><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
-    else k_inflate_q2<2, 0><<<grid, warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    k_inflate_q2<<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
 }
 
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,

@@ -59,47 +59,35 @@ BSG_HD uint32_t rev_bits(uint32_t code, uint32_t len) {
 // Bit reader over aligned 32-bit words with two words of look-ahead: peek() is one funnel shift, consume() is an
 // add plus a predicated word rotation whose load was issued a word earlier.  Positions are 32-bit word indices into
 // one 4-byte aligned buffer (the batch's compressed bytes), so the state is five 32-bit registers.
-// kPrefetch (device only, EXPERIMENT for round 2, never on in production): the two words of look-ahead hide an L1 hit
-// but not the one refill in 32 that opens a new 128-byte line of compressed input (ncu: ~14 % of the inflate kernel's
-// stall samples sit on the refill, profiles/r1b_k_inflate_hot_lines.md); 1 / 2 = prefetch the NEXT line into L1 / L2
-// whenever the reader enters a line.
-template <int kPrefetch>
-struct BitReaderT {
+struct BitReader {
     const uint32_t* base;  // the buffer (uniform for all blocks of a launch)
     uint32_t wi;           // index of the next word to load
     uint32_t w0, w1, w2, bo;
-    BSG_HD void prefetch_next_line() const {
-#if defined(__CUDA_ARCH__)
-        if (kPrefetch == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 32u));
-        if (kPrefetch == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + 32u));
-#endif
-    }
     BSG_HD void init(const uint32_t* buf, uint32_t byte_off) {
         base = buf;
         wi = byte_off >> 2;
         bo = (byte_off & 3u) * 8u;
         w0 = base[wi]; w1 = base[wi + 1]; w2 = base[wi + 2];
         wi += 3;
-        if (kPrefetch) prefetch_next_line();
     }
     BSG_HD uint32_t peek() const { return funnel_r(w0, w1, bo); }           // next 32 bits
     BSG_HD uint32_t peek_hi() const { return funnel_r(w1, w2, bo); }        // the 32 bits after those
     BSG_HD void consume_short(uint32_t n) {                                   // n <= 32
         bo += n;
-        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line(); }
+        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
     }
     BSG_HD void consume(uint32_t n) {                                         // n <= 64
         bo += n;
         if (bo >= 32) {
             bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++];
-            if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line();
-            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; if (kPrefetch && (wi & 31u) == 1u) prefetch_next_line(); }
+            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
         }
     }
     BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 32u + bo; }  // bits from the start of the buffer
     BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 4u + (bo >> 3); }   // only valid when bo is a multiple of 8
 };
-using BitReader = BitReaderT<0>;
+// (Measured and dropped in round 2, profiles/r2_ab_inflate_variants_*.json: prefetching the next 128-byte line of
+// compressed input into L1 / L2 whenever the reader enters a line: 72.9 / 72.5 vs 73.7 ms on C2, within noise.)
 
 struct Tables {
     uint16_t lit[1 << kLitBits];

@@ -99,13 +99,6 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
 
 namespace {
 
-// Ranges whose compressed gap is at most this many bytes are fused (fetching is block-granular).  0 = only ranges that
-// share or adjoin a BGZF block; larger values trade inflate work for fewer, longer segments.
-uint64_t fuse_gap() {
-    static const uint64_t g = getenv("BSG_FUSE_GAP") ? uint64_t(atoll(getenv("BSG_FUSE_GAP"))) : 0;
-    return g;
-}
-
 void scan_segment(const BamFile& bam, Segment* s) {
     uint64_t c = s->vbeg >> 16;
     const uint64_t cend = s->vend >> 16, uoff_end = s->vend & 0xffff;
@@ -166,7 +159,7 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
         if (r.end <= r.beg) continue;
         // Ranges that touch the same or neighbouring BGZF blocks are fused: fetching is block-granular, so a gap
         // shorter than a block would only make both neighbours inflate the shared blocks twice.
-        if (!merged.empty() && (r.beg >> 16) <= (merged.back().end >> 16) + fuse_gap())
+        if (!merged.empty() && (r.beg >> 16) <= (merged.back().end >> 16))
             merged.back().end = std::max(merged.back().end, r.end);
         else merged.push_back(r);
     }

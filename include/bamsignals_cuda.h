@@ -54,7 +54,9 @@ extern "C" {
 #define BSG_ENOMEM    -7   /* host or device allocation failed */
 #define BSG_EARG      -8   /* invalid argument ("negative 'ext' values don't make sense", :243, ...) */
 
-/* Execution options; none of them changes results.  Zero-initialise, set struct_size = sizeof(bsg_opts). */
+/* Execution options; none of them changes results.  Zero-initialise, set struct_size = sizeof(bsg_opts): every field's
+ * zero value is its default.  A library built against a longer or shorter version of the struct takes the first
+ * struct_size bytes and defaults for the rest; struct_size < 4 is BSG_EARG.  opts == NULL means all defaults. */
 typedef struct bsg_opts {
     int32_t struct_size;
     int32_t n_devices;        /* 0 = device 0 only; 1..16 = devices[0..n): regions (wide ones cut into bin-aligned pieces)
@@ -64,7 +66,8 @@ typedef struct bsg_opts {
     int32_t inflate_threads;  /* host inflate / record-walk workers; 0 = all hardware threads */
     int64_t batch_bytes;      /* uncompressed bytes per staged batch; 0 = default (1 GiB device inflate with a first batch
                                  of a quarter of that, 64 MiB host) */
-    int32_t verify_crc;       /* check BGZF CRC32 of every inflated block (htslib does); on by default */
+    int32_t verify_crc;       /* BGZF CRC32 of every inflated block is checked, as htslib does: 0 (default) or 1 = on,
+                                 -1 = off */
     int32_t use_cache;        /* reserved, must be 0 (open BAM handles and buffers are always reused across calls;
                                  record data is never cached: every call reads, inflates and decodes the file again) */
     int32_t gpu_inflate;      /* 0 (default) or 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the
@@ -119,7 +122,12 @@ int64_t bsg_output_layout(int64_t R, const int32_t* width, int32_t binsize, int3
  * kernel-only throughput is measured, and how an application amortises inflate over many parameter settings.
  * ext_hint is the halo fetched around every region, the `ext` of src/bamsignals.cpp:457,487: a staged call needs
  * |shift| (+ tlen_filter[1] when pe_mid) for pileups and tlen_filter[1] when tspan for coverage; a call that needs
- * more than the session was staged with is refused with BSG_EARG instead of silently missing reads. */
+ * more than the session was staged with is refused with BSG_EARG instead of silently missing reads.
+ * A session owns its resident device memory (returned by bsg_stage_close); several sessions may be open on one device
+ * and may be interleaved with each other and with bsg_pileup / bsg_coverage calls.  bsg_shutdown() ends every open
+ * session: later calls on its handle return BSG_EARG, bsg_stage_close() on it stays valid.
+ * out_offsets of every call must be the layout bsg_output_layout() gives for that call's binsize / ss (BSG_EARG
+ * otherwise): the result scatter trusts it. */
 typedef struct bsg_stage bsg_stage;
 int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* const* seq_levels, int32_t n_levels,
                    const int32_t* seq_idx, const int32_t* loc, const int32_t* width, const int8_t* strand,
@@ -157,7 +165,10 @@ int64_t bsg_debug_plan(const char* bampath, int64_t R, const char* const* seq_le
 const char* bsg_last_error(void);          /* valid until the next call on this thread */
 int  bsg_get_timings(bsg_timings* t);      /* of the last call on this thread */
 int  bsg_device_count(void);               /* CUDA devices visible (0 if none) */
-void bsg_shutdown(void);                   /* release cached device / pinned memory and worker threads */
+void bsg_shutdown(void);                   /* release cached device / pinned memory, worker threads, cached BAM handles
+                                              (the mmap of up to four recently used BAM files + their parsed indexes are
+                                              kept between calls while size and mtime are unchanged: do not truncate or
+                                              rewrite a BAM in place while a call on it is running) */
 const char* bsg_version(void);
 
 #ifdef __cplusplus

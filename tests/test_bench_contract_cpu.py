@@ -27,7 +27,11 @@ def test_reference_arm_line(tmp_path):
     assert d["value"] > 0 and abs(d["value"] - d["config"]["reads_in_bam"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     assert d["config"]["workload"].startswith("c2: bamProfile") and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    assert cb["kind"] == ("reference" if O.ref_available() else "port")      # oracle/_ref = the reference's own engine
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    assert d["configs"]["c1"]["cpu_ms_per_call_median"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "int32"
 

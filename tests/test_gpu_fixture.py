@@ -152,3 +152,84 @@ def test_staged_session_matches(fixture_bam):
         flat = st.coverage((0, 1000), 0, 66, -1, True)
         assert np.array_equal(flat, np.concatenate(O.coverage_core(fixture_bam, gr, (0, 1000), 0, 66, -1, True)))
         assert st.pileup(None, want_output=False) is None
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_sweep_vs_reference_code(fixture_bam):
+    """The CUDA path against the reference's OWN engine (oracle/_ref: src/bamsignals.cpp compiled unchanged) over the
+    whole sweep of tests/testthat/test_methods.R:33-104 on a stranded region set."""
+    gr = to_gr(spec_r.test_regions(seed=21, n=30))
+    for case in spec_r.sweep_pileup():
+        kw = dict(mapqual=case["mapqual"], shift=case["shift"], ss=case["ss"], paired_end=case["paired_end"],
+                  tlenFilter=case["tlenFilter"])
+        assert np.array_equal(B.bamCount(fixture_bam, gr, **kw), O.bamCount(fixture_bam, gr, impl="ref", **kw)), case
+        same_list(B.bamProfile(fixture_bam, gr, **kw).as_list(), O.bamProfile(fixture_bam, gr, impl="ref", **kw).as_list())
+    for case in spec_r.sweep_coverage():
+        kw = dict(mapqual=case["mapqual"], paired_end=case["paired_end"], tlenFilter=case["tlenFilter"])
+        same_list(B.bamCoverage(fixture_bam, gr, **kw).as_list(), O.bamCoverage(fixture_bam, gr, impl="ref", **kw).as_list())
+    for ff in (16, 1024, 1040, 0):
+        assert np.array_equal(B.bamCount(fixture_bam, gr, filteredFlag=ff), O.bamCount(fixture_bam, gr, filteredFlag=ff, impl="ref"))
+
+
+def test_interleaved_sessions_and_calls(fixture_bam):
+    """Two staged sessions on one device, interleaved with each other and with a plain call: each owns its resident
+    bytes; cached tiles are rebuilt when another call has replaced them on the device."""
+    gr_a = to_gr(spec_r.test_regions(seed=31, n=40))
+    gr_b = to_gr(spec_r.test_regions(seed=32, n=77))
+    gr_c = to_gr(spec_r.test_regions(seed=33, n=13))
+    want_a = np.concatenate([w.ravel(order="F") for w in O.pileup_core(fixture_bam, gr_a, None, 0, 1, 10, True)])
+    want_b = np.concatenate(O.coverage_core(fixture_bam, gr_b, None))
+    with B.Stage(fixture_bam, gr_a, ext_hint=10) as sa:
+        assert np.array_equal(sa.pileup(None, 0, 1, 10, True), want_a)
+        with B.Stage(fixture_bam, gr_b, ext_hint=0) as sb:
+            assert np.array_equal(sb.coverage(None), want_b)
+            assert np.array_equal(sa.pileup(None, 0, 1, 10, True), want_a)          # same parameters: cached tiles must be re-uploaded
+            same_list(B.bamProfile(fixture_bam, gr_c, binsize=7, ss=True).as_list(),
+                      O.bamProfile(fixture_bam, gr_c, binsize=7, ss=True).as_list())
+            assert np.array_equal(sb.coverage(None), want_b)
+            assert np.array_equal(sa.pileup(None, 0, 1, 10, True), want_a)
+        assert np.array_equal(sa.pileup(None, 0, 1, 10, True), want_a)              # after the other session is closed
+
+
+def test_shutdown_ends_open_sessions(fixture_bam):
+    gr = to_gr(spec_r.test_regions(seed=34, n=10))
+    st = B.Stage(fixture_bam, gr)
+    want = O.bamCount(fixture_bam, gr)
+    assert np.array_equal(st.pileup(None, binsize=-1), want)
+    B.lib().bsg_shutdown()
+    with pytest.raises(B.BamsignalsError) as e:
+        st.pileup(None, binsize=-1)
+    assert e.value.code == -8 and "bsg_shutdown" in str(e.value)
+    st.close()
+    assert np.array_equal(B.bamCount(fixture_bam, gr), want)                        # the library re-initialises itself
+
+
+def test_inconsistent_layout_is_refused(fixture_bam):
+    """out_offsets computed for another binsize / ss would make the result scatter overrun the caller's buffer."""
+    import ctypes as C
+    from bamsignals_b200 import api
+    gr = to_gr(spec_r.annot_regions())
+    m = api.marshal_regions(gr)
+    for off in (api.output_layout(m.width, 2, True), api.output_layout(m.width, 1, False)):
+        flat = np.zeros(int(api.output_layout(m.width, 1, True)[-1]), dtype=np.int32)
+        rc = B.lib().bsg_pileup(fixture_bam.encode(), m.R, m.levels, m.n_levels, api._p(m.seq_idx, C.c_int32),
+                                api._p(m.loc, C.c_int32), api._p(m.width, C.c_int32), api._p(m.strand, C.c_int8), None,
+                                0, 1, 0, 1, 0, -1, 0, 16385, api._p(flat, C.c_int32), api._p(off, C.c_int64), None, None)
+        assert rc == -8 and b"bsg_output_layout" in B.lib().bsg_last_error()
+        assert not flat.any()
+
+
+def test_opts_struct_versions(fixture_bam):
+    """A zero-initialised bsg_opts (struct_size set) means defaults - CRC check on; a shorter struct is a prefix."""
+    import ctypes as C
+    gr = to_gr(spec_r.annot_regions())
+    want = O.bamCount(fixture_bam, gr)
+    o = B.BsgOpts()
+    o.struct_size = C.sizeof(B.BsgOpts)
+    assert np.array_equal(B.bamCount(fixture_bam, gr, opts=o), want)
+    o.struct_size = 8                                   # struct_size + n_devices only
+    assert np.array_equal(B.bamCount(fixture_bam, gr, opts=o), want)
+    o.struct_size = 0
+    with pytest.raises(B.BamsignalsError) as e:
+        B.bamCount(fixture_bam, gr, opts=o)
+    assert e.value.code == -8

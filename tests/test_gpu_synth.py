@@ -263,3 +263,37 @@ def test_streaming_with_shuffled_and_overlapping_regions(gen_dir):
     same(B.bamCoverage(bam, gr, paired_end="extend", opts=o).as_list(), O.bamCoverage(bam, gr, paired_end="extend", nthreads=8).as_list())
     same(B.bamProfile(bam, gr, binsize=3, ss=True, shift=40, opts=o).as_list(), O.bamProfile(bam, gr, binsize=3, ss=True, shift=40, nthreads=8).as_list())
     assert np.array_equal(B.bamCount(bam, gr, ss=True, paired_end="midpoint", opts=o), O.bamCount(bam, gr, ss=True, paired_end="midpoint", nthreads=8))
+
+
+# ---- the default pipeline's own boundaries, crossed and compared with the oracle --------------------------------------
+def test_default_streaming_threshold_across_batch_boundaries(gen_dir):
+    """Everything at its DEFAULT except the batch size, which is the largest power of two below a third of the input, so
+    that the call crosses several batch boundaries (records straddling them included), the short first batch, and the
+    default 4 Mi-int streaming threshold (C2 at 1/50: 8 M result ints): what a full-size call does every 1 GiB."""
+    bam, info = WL.make_bam("c2", 0.02, gen_dir, unplaced=7)
+    gr, kw, fn = WL.regions("c2", 0.02)
+    want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    plan = B.debug_plan(bam, gr, ext=75, cap=1)
+    batch = 1 << (int(plan["bytes_inflated"] // 3).bit_length() - 1)
+    for inflate in (1, -1):
+        got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch, gpu_inflate=inflate), **kw)
+        t = B.timings()
+        assert np.array_equal(WL.as_flat(got), want), inflate
+        assert t["n_batches"] >= 3 and t["out_elems"] > (4 << 20)
+    got = getattr(B, fn)(bam, gr, **kw)                        # and the true default: one short first batch + the rest
+    assert np.array_equal(WL.as_flat(got), want)
+    if O.ref_available():                                      # the same job through the reference's own engine
+        assert np.array_equal(WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, impl="ref", **kw)), want)
+
+
+@pytest.mark.parametrize("preset,gs", [("c3", 0.01), ("c4", 0.004), ("c5", 0.004)])
+def test_default_options_mid_scale(gen_dir, preset, gs):
+    """C3 / C4 / C5 at a scale where a call has several default-sized streaming portions; all defaults."""
+    bam, _ = WL.make_bam(preset, gs, gen_dir, unplaced=7)
+    gr, kw, fn = WL.regions(preset, gs)
+    want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    plan = B.debug_plan(bam, gr, ext=1000, cap=1)
+    batch = 1 << (int(plan["bytes_inflated"] // 3).bit_length() - 1)
+    assert np.array_equal(WL.as_flat(getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch), **kw)), want)
+    assert B.timings()["n_batches"] >= 3
+    assert np.array_equal(WL.as_flat(getattr(B, fn)(bam, gr, **kw)), want)

@@ -17,15 +17,15 @@ for v in 1 2 4 5 6; do
     BSG_INFLATE_VARIANT=$v timeout 300 python -m pytest tests -m gpu -q -x -k "gpu_inflate or random_differential or fixture" 2>&1 | tail -2 > $O/r2_tests_variant$v.log
     echo "variant $v: $(tail -1 $O/r2_tests_variant$v.log)"
 done
-timeout 900 python tools/e2e_ab.py --preset c2 --reps 7 s2: s4:BSG_INFLATE_STREAMS=4 s1:BSG_INFLATE_STREAMS=1 \
+timeout 900 python tools/e2e_ab.py --preset c2 --reps 5 s2: s4:BSG_INFLATE_STREAMS=4 s1:BSG_INFLATE_STREAMS=1 \
     v1:BSG_INFLATE_VARIANT=1 v2:BSG_INFLATE_VARIANT=2 v4:BSG_INFLATE_VARIANT=4 v5:BSG_INFLATE_VARIANT=5 v6:BSG_INFLATE_VARIANT=6 \
     > $O/r2_ab_inflate_c2.json 2> $O/r2_ab.err
-timeout 900 python tools/e2e_ab.py --preset c4 --gscale 0.1 --reps 7 s2: s4:BSG_INFLATE_STREAMS=4 \
+timeout 900 python tools/e2e_ab.py --preset c4 --gscale 0.1 --reps 5 s2: s4:BSG_INFLATE_STREAMS=4 \
     v1:BSG_INFLATE_VARIANT=1 v2:BSG_INFLATE_VARIANT=2 v4:BSG_INFLATE_VARIANT=4 v5:BSG_INFLATE_VARIANT=5 v6:BSG_INFLATE_VARIANT=6 \
     > $O/r2_ab_inflate_c4_g0.1.json 2>> $O/r2_ab.err
 cat $O/r2_ab_inflate_c2.json $O/r2_ab_inflate_c4_g0.1.json
 # host-side experiment: a short LAST batch (engine.cu, BSG_SHORT_LAST=1) to shrink the count/copy/scatter tail of a call
-timeout 600 python tools/e2e_ab.py --preset c2 --reps 9 base: short_last:BSG_SHORT_LAST=1 > $O/r2_ab_short_last_c2.json 2>> $O/r2_ab.err
+timeout 600 python tools/e2e_ab.py --preset c2 --reps 5 base: short_last:BSG_SHORT_LAST=1 > $O/r2_ab_short_last_c2.json 2>> $O/r2_ab.err
 cat $O/r2_ab_short_last_c2.json
 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > $O/r2_racecheck.log 2>&1
 echo "racecheck rc=$?" >> $O/r2_racecheck.log

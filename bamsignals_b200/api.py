@@ -228,7 +228,7 @@ class BsgTimings(C.Structure):
     _fields_ = [("records", C.c_int64), ("records_kept", C.c_int64), ("bytes_compressed", C.c_int64),
                 ("bytes_inflated", C.c_int64), ("candidates", C.c_int64), ("out_elems", C.c_int64),
                 ("n_tiles", C.c_int64), ("n_batches", C.c_int64), ("n_launches", C.c_int64),
-                ("n_devices", C.c_int32), ("pad", C.c_int32),
+                ("n_devices", C.c_int32), ("upload_mode", C.c_int32),
                 ("ms_total", C.c_double), ("ms_plan", C.c_double), ("ms_fetch", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
                 ("ms_decode", C.c_double), ("ms_filter", C.c_double), ("ms_join", C.c_double),

@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -34,11 +35,20 @@ namespace {
 thread_local std::string g_err;
 thread_local bsg_timings g_tm;
 
+// NVTX range of one pipeline stage on the calling thread (header-only nvtx3: a no-op unless a profiler is attached)
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx&) = delete;
+};
+
+
 constexpr int kSlots = 4;                       // staging ring depth
 constexpr int64_t kDefaultBatch = 64ll << 20;   // uncompressed bytes per batch (host inflate)
-constexpr int64_t kDefaultGpuBatch = 1024ll << 20;   // uncompressed bytes per batch (GPU inflate)
+constexpr int64_t kDefaultGpuBatch = 2048ll << 20;   // byte cap of a device-inflate batch (the block-count "wave" is the working limit)
 constexpr size_t kCompChunk = 16u << 20;        // compressed bytes per pinned upload chunk (GPU inflate)
 constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
+constexpr uint64_t kSpanGap = 160u << 10;       // file gaps up to this many bytes are uploaded rather than skipped
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
 constexpr int kOutSlots = 3;                    // pinned result-staging ring
@@ -75,6 +85,7 @@ struct PinBuf {
 // Everything cached per device across calls (released by bsg_shutdown).
 struct DeviceCtx {
     int dev = 0;
+    int n_sm = 148;
     bool init = false;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr, s_hi = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
@@ -84,7 +95,7 @@ struct DeviceCtx {
     uint64_t tiles_gen = 0;                     // bumped whenever a Session uploads tiles: a staged Session's cached tiles are
                                                 // only valid while no other call has replaced them on this device
     DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
-    PinBuf h_total;
+    PinBuf h_total, h_desc[2];
     cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
     PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front;
     cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {}, ev_order = nullptr;
@@ -95,6 +106,7 @@ struct DeviceCtx {
         if (init && dev == device) { BSG_CUDA(cudaSetDevice(dev)); return; }
         dev = device;
         BSG_CUDA(cudaSetDevice(dev));
+        BSG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
@@ -152,7 +164,7 @@ struct DeviceCtx {
             cudaEventDestroy(ev_inflated[i]); cudaEventDestroy(ev_crc[i]);
         }
         for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev_pin[i]);
-        g_total.release(); h_total.release();
+        g_total.release(); h_total.release(); h_desc[0].release(); h_desc[1].release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
         cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
@@ -169,6 +181,56 @@ std::unique_ptr<Pool> g_pool;
 // mtime) reuses them.  Released by bsg_shutdown().
 std::vector<std::shared_ptr<BamFile>> g_bams;
 
+// ---- direct DMA from the page cache -------------------------------------------------------------------------------------
+// The compressed bytes of a call live in the BAM's read-only file mapping.  Staging them through pinned buffers costs a
+// CPU memcpy of every byte (measured: memcpy + H2D at 17-19 GB/s on 16 host threads, as long as the device inflate).
+// Instead, windows of the mapping are page-locked on first use (cudaHostRegister, read-only, portable) and stay so while
+// the handle is cached: the copy engine then reads the page cache itself.  Where the platform refuses (no read-only
+// registration, a filesystem whose pages cannot be pinned) the staging path is used.
+constexpr uint64_t kPinWindow = 128ull << 20;
+struct PinnedMapping {
+    std::vector<uint8_t> state;                 // per window: 0 = not tried, 1 = registered
+    bool unsupported = false;
+};
+std::mutex g_pin_mu;
+std::unordered_map<const BamFile*, PinnedMapping> g_pins;
+
+// true when [off, off + len) of the mapping is page-locked (registering the windows it touches if need be)
+bool ensure_pinned(const BamFile& bam, uint64_t off, uint64_t len) {
+    if (len == 0) return true;
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    PinnedMapping& pm = g_pins[&bam];
+    if (pm.unsupported) return false;
+    const uint64_t nwin = (bam.size() + kPinWindow - 1) / kPinWindow;
+    if (pm.state.size() != nwin) pm.state.assign(nwin, 0);
+    for (uint64_t w = off / kPinWindow; w <= (off + len - 1) / kPinWindow && w < nwin; ++w) {
+        if (pm.state[w]) continue;
+        const uint64_t beg = w * kPinWindow;
+        const uint64_t bytes = ((std::min(bam.size(), beg + kPinWindow) - beg) + 4095) & ~4095ull;     // whole pages of the mapping
+        Nvtx r("bsg:cudaHostRegister window");
+        const cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(bam.data()) + beg, bytes,
+                                               cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pm.unsupported = true;
+            if (getenv("BSG_DEBUG")) fprintf(stderr, "[bsg] cudaHostRegister of the BAM mapping refused (%s): staging through pinned chunks\n", cudaGetErrorString(e));
+            return false;
+        }
+        pm.state[w] = 1;
+    }
+    return true;
+}
+
+void unpin_mapping(const BamFile* bam) {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    auto it = g_pins.find(bam);
+    if (it == g_pins.end()) return;
+    for (size_t w = 0; w < it->second.state.size(); ++w)
+        if (it->second.state[w]) cudaHostUnregister(const_cast<uint8_t*>(bam->data()) + w * kPinWindow);
+    cudaGetLastError();
+    g_pins.erase(it);
+}
+
 std::shared_ptr<BamFile> open_bam(const char* path) {
     const std::string p = path ? path : "";
     struct stat st;
@@ -181,7 +243,7 @@ std::shared_ptr<BamFile> open_bam(const char* path) {
                 break;
             }
     }
-    auto b = std::make_shared<BamFile>(p);
+    std::shared_ptr<BamFile> b(new BamFile(p), [](BamFile* f) { unpin_mapping(f); delete f; });    // unpin before munmap
     if (g_bams.size() >= 4) g_bams.erase(g_bams.begin());
     g_bams.push_back(b);
     return b;
@@ -208,13 +270,6 @@ bsg_opts effective_opts(const bsg_opts* opts) {
     o.verify_crc = o.verify_crc < 0 ? 0 : 1;
     return o;
 }
-
-// NVTX range of one pipeline stage on the calling thread (header-only nvtx3: a no-op unless a profiler is attached)
-struct Nvtx {
-    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
-    ~Nvtx() { nvtxRangePop(); }
-    Nvtx(const Nvtx&) = delete;
-};
 
 struct Span { cudaEvent_t a, b; };
 struct KernelTimes {
@@ -320,17 +375,20 @@ public:
         batches_.clear();
         uint64_t max_batch = 0, total_bytes = 0, total_c = 0;
         int64_t rows_cap = 0;
+        // Device inflate: a launch keeps n_sm x 64 BGZF blocks in flight and its time is that of ONE block, however many
+        // streams are busy - so a batch is one such "wave" of blocks (~0.6 GB inflated on a B200), the first one half a
+        // wave (nothing overlaps its upload).  opts.batch_bytes > 0 overrides with a byte limit.
+        const uint64_t wave_blocks = (gpu && opts_.batch_bytes <= 0) ? uint64_t(inflate_wave_blocks(ctx_->n_sm)) : ~0ull;
         for (size_t i = 0; i < segs_.size();) {
             auto b = std::make_unique<Batch>();
             b->seg_first = i;
-            // (Measured: batches well below 1 GiB leave the inflate kernel with fewer BGZF blocks than the 148 x 56
-            // streams the GPU holds - a 128 MiB ... 1 GiB ramp cost C2 30 ms end to end.)  Only the FIRST batch is
-            // short: nothing overlaps its upload, so the device starts after a quarter of the usual copy.
             const bool first_short = gpu && !keep_raw && opts_.batch_bytes <= 0 && i == 0;
-            const uint64_t limit = first_short ? uint64_t(batch_bytes) / 4 : uint64_t(batch_bytes);
-            uint64_t acc = 0;
-            while (i < segs_.size() && (acc == 0 || acc + segs_[i].usize <= limit)) {
+            const uint64_t limit = uint64_t(batch_bytes);
+            const uint64_t limit_blocks = first_short ? wave_blocks / 2 : wave_blocks;
+            uint64_t acc = 0, nblk = 0;
+            while (i < segs_.size() && (acc == 0 || (acc + segs_[i].usize <= limit && nblk + segs_[i].blocks.size() <= limit_blocks))) {
                 acc += (segs_[i].usize + 15) & ~15ull;
+                nblk += segs_[i].blocks.size();
                 ++i;
             }
             b->seg_last = i;
@@ -926,7 +984,7 @@ private:
         hi_prio_ = !keep_raw_;
         BSG_CUDA(cudaEventRecord(c.ev_order, c.s_comp));
         BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_order, 0));
-        std::vector<Span> inflate_spans, walk_spans;
+        std::vector<Span> inflate_spans, walk_spans, h2d_spans;
         auto finish = [&](Pending& p) {
             if (!p.valid) return;
             BSG_CUDA(cudaEventSynchronize(c.ev_total[p.slot]));
@@ -978,12 +1036,25 @@ private:
             double tt = now_ms();
             nvtxRangePushA("bsg:batch descriptors");
             blocks.clear(); crcs.clear(); walkers.clear(); pieces.clear();
+            // Compressed layout of the batch on the device: SPANS of the file, each one contiguous byte range copied as it
+            // lies.  Consecutive segments whose gap in the file is small are one span (the gap's bytes ride along unused):
+            // one DMA descriptor costs about as much as 160 KB of transfer, and a job like C2 (100 k scattered windows)
+            // has 27 k segments of 45 KB with gaps of one to three BGZF blocks between them.
             uint64_t ubase = 0, cbase = 0;
             for (size_t k = b->seg_first; k < b->seg_last; ++k) {
                 const Segment& sg = segs_[k];
                 if (sg.blocks.empty()) continue;
                 const uint64_t fbeg = sg.blocks.front().coff, fend = sg.blocks.back().coff + sg.blocks.back().csize;
-                pieces.push_back(CopyPiece{fbeg, cbase, fend - fbeg});
+                uint64_t span_file, span_dst;
+                if (!pieces.empty() && fbeg >= pieces.back().file_off + pieces.back().len &&
+                    fbeg - (pieces.back().file_off + pieces.back().len) <= kSpanGap) {
+                    pieces.back().len = fend - pieces.back().file_off;
+                } else {
+                    cbase = (cbase + 15) & ~15ull;
+                    pieces.push_back(CopyPiece{fbeg & ~3ull, cbase, fend - (fbeg & ~3ull)});      // word-aligned source and destination
+                }
+                span_file = pieces.back().file_off; span_dst = pieces.back().dst_off;
+                cbase = span_dst + pieces.back().len;
                 uint64_t u = ubase;
                 // walkers: the segment start plus every index entry point strictly inside the segment
                 auto it = std::upper_bound(ent.begin(), ent.end(), sg.vbeg);
@@ -991,7 +1062,7 @@ private:
                 const uint32_t seg_end = uint32_t(ubase + sg.uend);
                 for (const BlockInfo& blk : sg.blocks) {
                     while (it != ent.end() && (*it >> 16) < blk.coff) ++it;      // stale entries cost parallelism, not correctness
-                    blocks.push_back(InflateBlock{uint32_t(cbase + (blk.coff - fbeg) + blk.hdr), blk.csize - blk.hdr - 8, uint32_t(u), blk.isize});
+                    blocks.push_back(InflateBlock{uint32_t(span_dst + (blk.coff - span_file) + blk.hdr), blk.csize - blk.hdr - 8, uint32_t(u), blk.isize});
                     crcs.push_back(blk.crc);
                     for (; it != ent.end() && *it < sg.vend && (*it >> 16) == blk.coff; ++it) {
                         const uint64_t uo = *it & 0xffff;
@@ -1003,8 +1074,8 @@ private:
                 }
                 if (seg_end > prev) walkers.push_back(make_uint2(prev, seg_end));
                 ubase += (sg.usize + 15) & ~15ull;
-                cbase += (fend - fbeg + 15) & ~15ull;
             }
+            if (cbase >= (1ull << 32) - 8192) fail(BSG_ENOMEM, "a batch's compressed bytes exceed 4 GiB");
             const uint32_t end_pos = walkers.empty() ? 0u : walkers.back().y;
             nvtxRangePop();
             t_desc += now_ms() - tt; tt = now_ms();
@@ -1033,10 +1104,24 @@ private:
                 d_raw = c.g_raw[slot].as<uint8_t>();
                 d_offs = c.g_offs[slot].as<uint32_t>();
             }
-            // ---- compressed bytes: file (page cache) -> pinned chunk -> device, chunk by chunk ----------------------------
-            // The pinned chunk mirrors a window [c_lo, c_lo + kCompChunk) of the device buffer byte for byte, so every
-            // chunk is ONE H2D copy no matter how many file pieces it holds.
-            {
+            // ---- compressed bytes -> device ------------------------------------------------------------------------------------
+            Span sph{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sph.a, c.s_copy));
+            bool direct = true;
+            for (const CopyPiece& pc : pieces) direct = direct && ensure_pinned(bam_, pc.file_off, pc.len);
+            if (direct) {
+                // the copy engine reads the page cache itself: one asynchronous copy per span (cut at 256 MB so that a
+                // long span does not sit in front of the descriptor copies of this batch for longer than it must)
+                for (const CopyPiece& pc : pieces)
+                    for (uint64_t o = 0; o < pc.len; o += (256ull << 20)) {
+                        const uint64_t n = std::min<uint64_t>(256ull << 20, pc.len - o);
+                        BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + pc.dst_off + o, bam_.data() + pc.file_off + o, n, cudaMemcpyHostToDevice, c.s_copy));
+                    }
+                tm_.upload_mode = 1;
+            } else {
+                // Staging: file (page cache) -> pinned chunk -> device, chunk by chunk.  The pinned chunk mirrors a window
+                // [c_lo, c_lo + kCompChunk) of the device buffer byte for byte, so every chunk is ONE H2D copy no matter how
+                // many spans it holds.
                 struct Part { const uint8_t* src; uint64_t pin_off, len; };
                 size_t pi = 0; uint64_t done_in_piece = 0;
                 while (pi < pieces.size()) {
@@ -1072,11 +1157,23 @@ private:
                     BSG_CUDA(cudaEventRecord(c.ev_pin[ps], c.s_copy));
                 }
             }
-            if (!blocks.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_blocks[slot].p, blocks.data(), blocks.size() * sizeof(InflateBlock), cudaMemcpyHostToDevice, c.s_copy));
-            if (!crcs.empty() && opts_.verify_crc) BSG_CUDA(cudaMemcpyAsync(c.g_crc[slot].p, crcs.data(), crcs.size() * 4, cudaMemcpyHostToDevice, c.s_copy));
-            if (!walkers.empty()) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, walkers.data(), walkers.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.s_copy));
+            // descriptors go through a pinned buffer of the slot (its previous use ended with the batch before last, whose
+            // kernels the wait above covers), so nothing here blocks the host
+            {
+                const size_t nb_b = blocks.size() * sizeof(InflateBlock), nb_c = crcs.size() * 4, nb_w = walkers.size() * sizeof(uint2);
+                const size_t o_c = (nb_b + 63) & ~size_t(63), o_w = o_c + ((nb_c + 63) & ~size_t(63));
+                c.h_desc[slot].ensure(o_w + nb_w + 64);
+                uint8_t* hd = c.h_desc[slot].as<uint8_t>();
+                if (nb_b) memcpy(hd, blocks.data(), nb_b);
+                if (nb_c) memcpy(hd + o_c, crcs.data(), nb_c);
+                if (nb_w) memcpy(hd + o_w, walkers.data(), nb_w);
+                if (nb_b) BSG_CUDA(cudaMemcpyAsync(c.g_blocks[slot].p, hd, nb_b, cudaMemcpyHostToDevice, c.s_copy));
+                if (nb_c && opts_.verify_crc) BSG_CUDA(cudaMemcpyAsync(c.g_crc[slot].p, hd + o_c, nb_c, cudaMemcpyHostToDevice, c.s_copy));
+                if (nb_w) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, hd + o_w, nb_w, cudaMemcpyHostToDevice, c.s_copy));
+            }
             BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
-            BSG_CUDA(cudaStreamSynchronize(c.s_copy));                 // blocks/walkers vectors are reused next iteration
+            BSG_CUDA(cudaEventRecord(sph.b, c.s_copy));
+            h2d_spans.push_back(sph);
             nvtxRangePop();
             t_copy += now_ms() - tt; tt = now_ms();
             nvtxRangePushA("bsg:launch inflate + crc + walk");
@@ -1130,7 +1227,7 @@ private:
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_hi));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
-        tm_.ms_h2d = t_copy;
+        tm_.ms_h2d = sum_ms(h2d_spans);         // on the copy stream: the time the copy engine (and, when staging, the pool) needed
         if (getenv("BSG_DEBUG"))
             fprintf(stderr, "[bsg] gpu pipeline host ms: descriptors %.1f, slot wait %.1f, memcpy+h2d %.1f, finish(wait total) %.1f; device inflate %.1f, walk %.1f\n",
                     t_desc, t_wait, t_copy, t_finish, tm_.ms_inflate_gpu, sum_ms(walk_spans));

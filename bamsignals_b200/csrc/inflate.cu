@@ -2,19 +2,25 @@
 // file and ships COMPRESSED bytes; raw-DEFLATE decoding of every BGZF block, its integrity check and the block_size
 // chain walk run on the device.
 //
-// k_inflate_q2: one warp per TWO BGZF blocks (RFC 1951 streams, <= 64 KiB out each), two alternating phases per round
-//   of <= 128 symbols: lanes 0 and 16 decode Huffman symbols of their streams into shared-memory token queues, then
-//   all 32 lanes materialise one queue after the other (warp scan of token lengths -> output positions; all literals
-//   of a 32-token chunk in one store; independent short matches replayed concurrently, one lane each).
+// k_inflate_ws: warp-specialised.  One persistent CTA per SM holds 64 BGZF blocks (RFC 1951 streams, <= 64 KiB out each)
+//   at a time: the 64 lanes of warps 0-1 each decode the Huffman symbols of ONE stream into a shared-memory token queue
+//   (32 tokens per round), warps 2-15 turn the queues of the previous round into bytes (warp scan of token lengths ->
+//   output positions; all literals of a queue in one store; independent short matches replayed concurrently, one lane
+//   each).  The two halves overlap through double-buffered queues and ONE CTA barrier per round.
 // k_crc32: one warp per block: 32 slicing-by-4 pieces folded with carry-less multiplies.
 // k_walk<>: one thread per index entry point (BAI linear-index offsets and chunk bounds are record-aligned); each
 //   walks block_size -> next record until the next entry point; a scan of the counts in between gives every walker
 //   its slice of the offsets array (count pass, scan, write pass; no atomics, deterministic order).
 //
-// Designs measured and dropped in round 1 (C2, 5.26 GB inflated, B200): per-symbol warp round trip
-// (k_inflate v1: 150 ms), first token-queue version (144 ms), D = 4/8/16 lock-step streams per warp with group
-// copies (142-282 ms), one stream per lane (235 ms: ~10 active lanes, 3 warps/SM, latency-bound).  This kernel: 127 ms.
+// Designs measured and dropped (C2, B200): round 1: per-symbol warp round trip (150 ms), D = 4/8/16
+// lock-step streams per warp with group copies (142-282 ms), one stream per lane doing its own copies (235 ms), one warp
+// per TWO streams alternating between a decode phase on lanes 0/16 and a warp-wide copy phase (73.7 ms; one stream 82.8,
+// four 99.2; next-line prefetch of the compressed input and loads-first match copies: no gain,
+// profiles/r2_ab_inflate_variants_c2.json).  ncu on that kernel: 70 warp instructions per token with 1.6 active lanes in
+// the decode phase - the lanes were the wasted resource, hence one stream per LANE here.
 #include "kernels.cuh"
+
+#include <algorithm>
 
 #include "inflate_core.cuh"
 
@@ -24,27 +30,26 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_inflate_q2: the production inflate kernel.  Two-phase rounds on the lean decode core of inflate_core.cuh (32-bit
-// look-ahead bit reader, one table lookup per code, one 64-bit look-ahead per match, sticky error flag instead of
-// divergent breaks) and a materialisation step with one predicated load/store per <= 32-byte match.
-//
-// TWO streams per warp: lanes 0 and 16 each decode their own BGZF block in the same instructions (phase 1 is a
-// serial dependency chain per stream - 72 % of the kernel's issue slots with one active lane - so a second chain in
-// the same warp is almost free); phase 2 then replays the two queues one after the other with all 32 lanes.
-// 16-bit table entries keep a stream at 3.7 KB of shared memory, so 28 warps = 56 streams are resident per SM.
-// The decode core is unit-tested on the host (tests/host_inflate_harness.cpp) against zlib's CRC32.
+// k_inflate_ws
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kQ2Warps = 4;
-#ifndef BSG_Q2_MINB
-#define BSG_Q2_MINB 7
-#endif
-// (Round 2, profiles/r2_ab_inflate_variants_*.json: ONE stream per warp 82.8 ms, FOUR streams per warp at half the warps
-// 99.2 ms against 73.7 ms for two - with fewer warps the serialised queues of phase 2 are no longer hidden.)
-constexpr int kStreams = 2;
-struct Q2Smem {
+constexpr int kWsDecWarps = 2;                       // warps whose 32 lanes decode one stream each
+constexpr int kWsStreams = kWsDecWarps * 32;         // streams resident per CTA (= per SM)
+constexpr int kWsCopyWarps = 14;                     // warps that materialise the token queues
+constexpr int kWsThreads = (kWsDecWarps + kWsCopyWarps) * 32;
+
+struct WsStream {
     inflate_core::Tables T;
-    uint32_t q[inflate_core::kQueue];
+    uint32_t q[2][inflate_core::kQueue];             // token queues of the round being decoded / being materialised
 };
+struct WsCtl {
+    uint32_t qn[2][kWsStreams];                      // tokens in q[buf] of every stream
+    uint32_t pos[kWsStreams];                        // bytes materialised so far (owned by the stream's copy warp)
+    uint32_t out_off[kWsStreams], out_len[kWsStreams];
+    uint32_t produced[2][kWsDecWarps];               // did the decode warp hand over anything in round buf?
+};
+constexpr size_t kWsSmem = sizeof(WsStream) * kWsStreams + sizeof(WsCtl);
+static_assert(sizeof(WsStream) % 8 == 0, "stream slots keep the tables aligned");
+static_assert(kWsSmem <= 227 * 1024, "one CTA per SM must fit the opt-in shared memory");
 
 // fill_queue's table lookups and queue stores through explicit shared-space addresses (kept in registers)
 struct SmemAccess {
@@ -88,171 +93,193 @@ struct SmemAccess {
     }
 };
 
-// Phase 2: all 32 lanes materialise one stream's token queue q[0..nq) behind out[pos_base); returns the new pos_base.
-// (Round 2: issuing all loads of a non-overlapping short match before its first store was measured at 73.1 vs 73.7 ms -
-// no gain, dropped.)
-__device__ __forceinline__ uint32_t materialise(const volatile uint32_t* q, int nq, uint8_t* out, uint32_t pos_base, int lane) {
-    using namespace inflate_core;
-    for (int base = 0; base < nq; base += 32) {
-        const bool valid = base + lane < nq;
-        const uint32_t t = valid ? q[base + lane] : 0u;
-        const bool is_match = (t >> 31) != 0;
-        const bool is_skip = !is_match && (t & kTokSkip);
-        const uint32_t len = is_match ? (t & 0x1ffu) : (is_skip ? (t & 0xffffffu) : (valid ? 1u : 0u));
-        uint32_t incl = len;
+// One queue (<= 32 tokens, one per lane) -> bytes behind out[pos_base); returns the new pos_base.
+__device__ __forceinline__ uint32_t materialise(const uint32_t* q, int nq, uint8_t* out, uint32_t pos_base, int lane) {
+    const bool valid = lane < nq;
+    const uint32_t t = valid ? q[lane] : 0u;
+    const bool is_match = (t >> 31) != 0;
+    const uint32_t len = is_match ? (t & 0x1ffu) : (valid ? 1u : 0u);
+    uint32_t incl = len;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += up;
-        }
-        const uint32_t pos = pos_base + incl - len;
-        if (valid && !is_match && !is_skip) out[pos] = uint8_t(t);
-        // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
-        // first pending token reads only finished output, so all of them are copied at once, each by its own lane
-        // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
-        // they reach the front.
-        uint32_t pending = __ballot_sync(FULL, is_match);
-        const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
-        const bool is_long = is_match && own_len > 32u;
-        const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
-        __syncwarp();
-        while (pending) {
-            const int first = __ffs(pending) - 1;
-            const uint32_t front = __shfl_sync(FULL, pos, first);
-            if (__shfl_sync(FULL, uint32_t(is_long), first)) {
-                const uint32_t mt = __shfl_sync(FULL, t, first);
-                const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
-                uint8_t* dst = out + front;
-                {   // the first 32 bytes never depend on bytes written in this step
-                    const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
-                    dst[lane] = dst[so];
-                }
-                // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
-                const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
-                for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
-                    __syncwarp();
-                    if (j < mlen) dst[j] = dst[int(j) - int(K)];
-                }
-                pending &= ~(1u << first);
-                __syncwarp();
-                continue;
-            }
-            const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
-            if (ready) {
-                for (uint32_t done = 0; done < own_len; done += 8u) {
-                    const uint32_t n = min(own_len - done, 8u);
-                    uint8_t* d = out + pos + done;
-                    if (pos + done >= 8u) {
-                        // eight source bytes from three aligned words + two funnel shifts (raw is cudaMalloc'ed; the
-                        // bytes around [sp, sp + 8) that the words also cover are finished output or slack)
-                        const uint8_t* sp = d - max(own_dist, 8u);
-                        const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-                        const uint32_t sh = uint32_t(sa & 3u) * 8u;
-                        const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2];
-                        const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                        uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
-                        if (own_dist < 8u) {
-                            uint64_t rep = w >> (8u * (8u - own_dist));
-                            for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
-                            w = rep;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
-                    } else {
-                        for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
-                    }
-                }
-            }
-            pending &= ~__ballot_sync(FULL, ready);
-            __syncwarp();
-        }
-        pos_base += __shfl_sync(FULL, incl, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
     }
-    return pos_base;
+    const uint32_t pos = pos_base + incl - len;
+    if (valid && !is_match) out[pos] = uint8_t(t);
+    // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
+    // first pending token reads only finished output, so all of them are copied at once, each by its own lane
+    // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
+    // they reach the front.
+    uint32_t pending = __ballot_sync(FULL, is_match);
+    const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
+    const bool is_long = is_match && own_len > 32u;
+    const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
+    __syncwarp();
+    while (pending) {
+        const int first = __ffs(pending) - 1;
+        const uint32_t front = __shfl_sync(FULL, pos, first);
+        if (__shfl_sync(FULL, uint32_t(is_long), first)) {
+            const uint32_t mt = __shfl_sync(FULL, t, first);
+            const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
+            uint8_t* dst = out + front;
+            {   // the first 32 bytes never depend on bytes written in this step
+                const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
+                dst[lane] = dst[so];
+            }
+            // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
+            const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
+            for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
+                __syncwarp();
+                if (j < mlen) dst[j] = dst[int(j) - int(K)];
+            }
+            pending &= ~(1u << first);
+            __syncwarp();
+            continue;
+        }
+        const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
+        if (ready) {
+            for (uint32_t done = 0; done < own_len; done += 8u) {
+                const uint32_t n = min(own_len - done, 8u);
+                uint8_t* d = out + pos + done;
+                if (pos + done >= 8u) {
+                    // eight source bytes from three aligned words + two funnel shifts (raw is cudaMalloc'ed; the
+                    // bytes around [sp, sp + 8) that the words also cover are finished output or slack)
+                    const uint8_t* sp = d - max(own_dist, 8u);
+                    const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+                    const uint32_t sh = uint32_t(sa & 3u) * 8u;
+                    const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2];
+                    const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                    uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
+                    if (own_dist < 8u) {
+                        uint64_t rep = w >> (8u * (8u - own_dist));
+                        for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
+                        w = rep;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
+                } else {
+                    for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
+                }
+            }
+        }
+        pending &= ~__ballot_sync(FULL, ready);
+        __syncwarp();
+    }
+    return pos_base + __shfl_sync(FULL, incl, 31);
 }
 
-__global__ void __launch_bounds__(kQ2Warps * 32, BSG_Q2_MINB) k_inflate_q2(const InflateBlock* __restrict__ blocks, int n_blocks,
-                                                                        const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
+__global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock* __restrict__ blocks, int n_blocks,
+                                                              const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
     using namespace inflate_core;
-    constexpr int kWarps = kQ2Warps;
-    constexpr int kLanes = 32 / kStreams;                    // lanes per stream in phase 1; the first of them decodes
-    __shared__ Q2Smem s_mem[kWarps][kStreams];
+    extern __shared__ __align__(16) uint8_t ws_smem[];
+    WsStream* S = reinterpret_cast<WsStream*>(ws_smem);
+    WsCtl& ctl = *reinterpret_cast<WsCtl*>(ws_smem + sizeof(WsStream) * kWsStreams);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / kLanes;                           // the stream this lane belongs to in phase 1
-    const bool dec = (lane & (kLanes - 1)) == 0;             // lanes 0 and 16 decode
-    const int b = (blockIdx.x * kWarps + wid) * kStreams + sub;
-    if ((blockIdx.x * kWarps + wid) * kStreams >= n_blocks) return;       // whole warp idle
-    Tables& T = s_mem[wid][sub].T;
-    volatile uint32_t* q = s_mem[wid][sub].q;
-    SmemAccess acc{uint32_t(__cvta_generic_to_shared(s_mem[wid][sub].T.lit)), 0u, 0u};
-    // identity shuffle: ptxas cannot re-derive the value from %tid inside the decode loop (it otherwise rebuilds the
-    // address with six instructions per token); dist and q are fixed offsets from it
-    acc.lit_a = __shfl_sync(FULL, acc.lit_a, lane);
-    acc.dist_a = acc.lit_a + uint32_t(sizeof(uint16_t) << kLitBits);
-    acc.q_a = acc.lit_a + uint32_t(sizeof(Tables));
-    bool fin = b >= n_blocks;                               // this lane's stream is finished (or absent)
-    InflateBlock blk{0u, 0u, 0u, 0u};
-    if (!fin) blk = blocks[b];
-    uint8_t* out = raw + blk.out_off;
-    const uint32_t out_len = blk.out_len;
-    BitReader br;
-    br.base = reinterpret_cast<const uint32_t*>(comp);     // cudaMalloc'ed: aligned
-    br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
-    if (dec && !fin) br.init(br.base, blk.in_off);
-    const uint64_t end_bit = (uint64_t(blk.in_off) + blk.in_len) * 8u;
-    uint32_t op_dec = 0, pos_base = 0;
-    int phase = 0, last = 0;
-    for (;;) {
-        int nq = 0, state = fin ? 3 : 0;       // state: 0 = go on, 1 = stream finished, 2 = error, 3 = nothing to do
-        if (dec && !fin) {
-            if (phase == 0) {
-                const int h = read_block_header(br, T, reinterpret_cast<uint8_t*>(const_cast<uint32_t*>(q)), &last);
-                if (h == 2) state = 2;
-                else if (h == 1) {
-                    br.consume((32u - br.bo) & 7u);
-                    const uint32_t v = br.peek();
-                    br.consume(32);
-                    const uint32_t len = v & 0xffffu, nlen = v >> 16;
-                    const uint32_t src_off = br.byte_pos();
-                    if ((len ^ nlen) != 0xffffu || op_dec + len > out_len || (uint64_t(src_off) + len) * 8u > end_bit) state = 2;
-                    else {
-                        const uint8_t* src = comp + src_off;
-                        for (uint32_t j = 0; j < len; ++j) out[op_dec + j] = src[j];
-                        op_dec += len;
-                        br.init(br.base, src_off + len);
-                        q[0] = kTokSkip | len;
-                        nq = 1;
-                        if (last) state = 1;
+    const bool is_dec = wid < kWsDecWarps;
+    const int s = threadIdx.x;                               // decode lanes: threads 0..63 own streams 0..63
+    // Generations: the CTA takes 64 consecutive blocks at a time; all 64 streams of a generation start together, so that
+    // the (serial, per-lane) block-header parse and table build run in all lanes at once.
+    for (int gen = 0;; ++gen) {
+        const int b0 = (gen * int(gridDim.x) + int(blockIdx.x)) * kWsStreams;
+        if (b0 >= n_blocks) break;
+        bool fin = true;
+        InflateBlock blk{0u, 0u, 0u, 0u};
+        BitReader br;
+        br.base = reinterpret_cast<const uint32_t*>(comp);  // cudaMalloc'ed: aligned
+        br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
+        SmemAccess acc{0u, 0u, 0u};
+        if (is_dec) {
+            fin = b0 + s >= n_blocks;
+            if (!fin) { blk = blocks[b0 + s]; br.init(br.base, blk.in_off); }
+            ctl.out_off[s] = blk.out_off; ctl.out_len[s] = blk.out_len; ctl.pos[s] = 0;
+            ctl.qn[0][s] = 0; ctl.qn[1][s] = 0;
+            acc.lit_a = uint32_t(__cvta_generic_to_shared(S[s].T.lit));
+            // identity shuffle: ptxas cannot re-derive the value from %tid inside the decode loop (it otherwise rebuilds
+            // the address with several instructions per token); dist and the queues are fixed offsets from it
+            acc.lit_a = __shfl_sync(FULL, acc.lit_a, lane);
+            acc.dist_a = acc.lit_a + uint32_t(sizeof(uint16_t) << kLitBits);
+        }
+        const uint32_t out_len = blk.out_len;
+        const uint64_t end_bit = (uint64_t(blk.in_off) + blk.in_len) * 8u;
+        uint32_t op_dec = 0;
+        int phase = 0, last = 0;
+        __syncthreads();
+        for (int r = 0;; ++r) {
+            const int buf = r & 1;
+            if (is_dec) {
+                // ---- one round of one stream per lane: <= kQueue tokens into q[buf] ------------------------------------
+                int nq = 0, state = 0;               // state: 0 = go on, 1 = stream finished, 2 = error
+                if (!fin) {
+                    uint32_t* q = S[s].q[buf];
+                    acc.q_a = acc.lit_a + uint32_t(sizeof(Tables)) + uint32_t(buf) * uint32_t(sizeof(uint32_t) * kQueue);
+                    if (phase == 0) {
+                        const int h = read_block_header(br, S[s].T, reinterpret_cast<uint8_t*>(q), &last);
+                        if (h == 2) state = 2;
+                        else if (h == 1) {           // stored block: LEN, NLEN, then LEN bytes that a copy warp moves
+                            br.consume((32u - br.bo) & 7u);
+                            const uint32_t v = br.peek();
+                            br.consume(32);
+                            const uint32_t len = v & 0xffffu, nlen = v >> 16;
+                            const uint32_t src_off = br.byte_pos();
+                            if ((len ^ nlen) != 0xffffu || op_dec + len > out_len || (uint64_t(src_off) + len) * 8u > end_bit) state = 2;
+                            else {
+                                op_dec += len;
+                                br.init(br.base, src_off + len);
+                                q[0] = kTokSkip | len;
+                                q[1] = src_off;
+                                nq = 2;
+                                if (last) state = 1;
+                            }
+                        } else phase = 1;
                     }
-                } else phase = 1;
+                    if (phase == 1 && nq == 0 && state == 0) {
+                        int eob = 0, bad = 0;
+                        nq = fill_queue(br, acc, &op_dec, &eob, &bad);
+                        if (eob) { phase = 0; if (last) state = 1; }
+                        if (bad || op_dec > out_len || br.bit_pos() > end_bit) state = 2;
+                    }
+                    if (state == 2) nq = 0;          // a broken round is discarded; the status flag reports it
+                    if (state != 0) {
+                        if (state == 2 || op_dec != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
+                        fin = true;
+                    }
+                }
+                ctl.qn[buf][s] = uint32_t(nq);
+                const bool any = __any_sync(FULL, nq > 0);
+                if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
+            } else if (r > 0) {
+                // ---- the queues of the previous round -> bytes ------------------------------------------------------------
+                const int pb = buf ^ 1;
+                for (int k = wid - kWsDecWarps; k < kWsStreams; k += kWsCopyWarps) {
+                    const int nq = int(ctl.qn[pb][k]);
+                    if (nq == 0) continue;                                         // warp-uniform
+                    const uint32_t* q = S[k].q[pb];
+                    uint8_t* out = raw + ctl.out_off[k];
+                    uint32_t pos = ctl.pos[k];
+                    const uint32_t t0 = q[0];
+                    if (nq == 2 && !(t0 >> 31) && (t0 & kTokSkip)) {               // stored block: copy from the compressed buffer
+                        const uint32_t len = t0 & 0xffffu;
+                        const uint8_t* src = comp + q[1];
+                        for (uint32_t j = lane; j < len; j += 32) out[pos + j] = src[j];
+                        pos += len;
+                    } else {
+                        pos = materialise(q, nq, out, pos, lane);
+                    }
+                    __syncwarp();
+                    if (lane == 0) ctl.pos[k] = pos;
+                }
             }
-            if (phase == 1 && nq == 0 && state == 0) {
-                int eob = 0, bad = 0;
-                nq = fill_queue(br, acc, &op_dec, &eob, &bad);
-                if (eob) { phase = 0; if (last) state = 1; }
-                if (bad || op_dec > out_len || br.bit_pos() > end_bit) state = 2;
-            }
-        }
-        __syncwarp();
-        // ---- phase 2: materialise the two queues, one after the other, with the whole warp ------------------------------
+            __syncthreads();
+            bool more = false;
 #pragma unroll
-        for (int s = 0; s < kStreams; ++s) {
-            const int src = kLanes * s;
-            const int st_s = __shfl_sync(FULL, state, src);
-            const int nq_s = __shfl_sync(FULL, nq, src);
-            const uint32_t pb_s = __shfl_sync(FULL, pos_base, src);
-            const uint32_t oo_s = __shfl_sync(FULL, blk.out_off, src);
-            if (st_s >= 2 || nq_s == 0) continue;            // warp-uniform
-            const uint32_t pb_new = materialise(s_mem[wid][s].q, nq_s, raw + oo_s, pb_s, lane);
-            if (lane == src) pos_base = pb_new;
+            for (int w = 0; w < kWsDecWarps; ++w) more = more || ctl.produced[buf][w] != 0;
+            if (!more) break;                        // nothing was handed over in round r: round r - 1 was the last one
         }
-        __syncwarp();
-        if (dec && !fin && state != 0) {
-            if (state == 2 || op_dec != out_len || pos_base != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
-            fin = true;
-        }
-        if (__all_sync(FULL, fin || !dec)) break;
+        // every stream must have produced exactly ISIZE bytes
+        if (threadIdx.x < kWsStreams && b0 + s < n_blocks && ctl.pos[s] != ctl.out_len[s]) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
+        __syncthreads();                             // the next generation re-initialises the control block
     }
 }
 
@@ -401,10 +428,19 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s) {
     if (n_blocks <= 0) return;
-    const int per_cta = kQ2Warps * kStreams;
-    const int grid = (n_blocks + per_cta - 1) / per_cta;
-    k_inflate_q2<<<grid, kQ2Warps * 32, 0, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    static thread_local int sms[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && sms[dev] == 0) {
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_inflate_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWsSmem));
+    }
+    const int n_sm = (dev >= 0 && dev < 16 && sms[dev] > 0) ? sms[dev] : 148;
+    const int grid = std::min(n_sm, (n_blocks + kWsStreams - 1) / kWsStreams);     // persistent: one CTA per SM
+    k_inflate_ws<<<grid, kWsThreads, kWsSmem, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
 }
+
+int inflate_wave_blocks(int n_sm) { return n_sm * kWsStreams; }
 
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s) {

@@ -1,9 +1,9 @@
 // Single-lane DEFLATE decode core shared by the GPU inflate kernel and its host-side unit harness
 // (tests/host_inflate_harness.cpp compiles this header with a plain C++ compiler).  Everything here is executed by ONE
-// thread per BGZF block: bit reader, decode-table construction, and "phase 1" = Huffman symbols -> token queue.
+// thread per BGZF block: bit reader, decode-table construction, and Huffman symbols -> token queue.
 //
-// Shared-memory budget: 3776 bytes per stream (16-bit table entries, 128-token queue that doubles as the code-length
-// scratch while a block header is parsed), so that two streams per warp still leave 28 warps resident per SM.
+// Shared-memory budget: 3272 bytes of tables per stream (16-bit entries; the distance table doubles as the code-length
+// scratch while a block header is parsed) + two 32-token queues = 3528 bytes, so that 64 streams fit one SM.
 #pragma once
 #include <cstdint>
 
@@ -20,7 +20,7 @@ namespace inflate_core {
 #define BSG_LIT_BITS 10
 #endif
 constexpr int kLitBits = BSG_LIT_BITS, kDistBits = 8;
-constexpr int kQueue = 128;
+constexpr int kQueue = 32;           // tokens a stream hands over per round
 
 // token: literal = byte ; match = 1 << 31 | (dist - 1) << 16 | len ; skip (stored bytes already in place) = 1 << 30 | len
 constexpr uint32_t kTokMatch = 0x80000000u, kTokSkip = 0x40000000u;
@@ -99,7 +99,8 @@ struct Tables {
     uint16_t lit_first, lit_index, dist_first, dist_index;
 };
 constexpr int kLensBytes = 320;     // code lengths of one block header: 288 literal/length + 32 distance symbols
-static_assert(kQueue * 4 >= kLensBytes, "the token queue doubles as the code-length scratch");
+static_assert(sizeof(uint16_t) << kDistBits >= kLensBytes, "the distance table doubles as the code-length scratch");
+static_assert(kQueue * 4 >= 32, "the (empty) token queue holds the 32 distance code lengths while the tables are built");
 
 BSG_HD uint32_t lit_entry(int sym, int len) {
     if (sym < 256) return uint32_t(len) | (uint32_t(sym) << 8);
@@ -205,10 +206,12 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint16_t* primary, int bits,
 }
 
 // Block header: reads BFINAL/BTYPE and, for Huffman blocks, the code lengths, then builds the tables.
-// `lens` is kLensBytes of scratch (the kernel lends the empty token queue).
+// The code lengths are collected in the (not yet built) distance table; `dlens` is 32 bytes of scratch for the distance
+// code lengths while the distance table is written (the kernel lends the empty token queue).
 // Returns 0 = Huffman block ready, 1 = stored block (caller handles LEN/NLEN), 2 = error.
 template <class BR>
-BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* lens, int* last) {
+BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* dlens, int* last) {
+    uint8_t* lens = reinterpret_cast<uint8_t*>(T.dist);
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     uint32_t v = br.peek();
     *last = int(v & 1u);
@@ -264,8 +267,9 @@ BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* lens, int* last) {
         for (int k = ndist - 1; k >= 0; --k) lens[288 + k] = lens[nlit + k];
         for (int k = nlit; k < 288; ++k) lens[k] = 0;
     }
+    for (int k = 0; k < 32; ++k) dlens[k] = lens[288 + k];
     bool ok = build_table(lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, false, &T.lit_first, &T.lit_index);
-    ok = build_table(lens + 288, ndist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true, &T.dist_first, &T.dist_index) && ok;
+    ok = build_table(dlens, ndist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true, &T.dist_first, &T.dist_index) && ok;
     return ok ? 0 : 2;
 }
 

@@ -83,6 +83,9 @@ struct InflateBlock {
 };
 void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
                     cudaStream_t s);
+// BGZF blocks one launch keeps in flight on a device with n_sm SMs: batches that are a multiple of this leave no partly
+// filled last generation.
+int inflate_wave_blocks(int n_sm);
 // CRC32 of every inflated block against the BGZF trailer (d_crc[i] belongs to d_blocks[i]).
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s);

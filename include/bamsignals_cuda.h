@@ -90,7 +90,8 @@ typedef struct bsg_timings {
     int64_t n_batches;
     int64_t n_launches;       /* kernels launched by this library during the call */
     int32_t n_devices;
-    int32_t pad;
+    int32_t upload_mode;      /* device inflate: 1 = compressed bytes DMA'd straight from the page-locked file mapping,
+                                 0 = staged through pinned chunks by the worker pool (or host inflate) */
     double ms_total, ms_plan, ms_fetch, ms_h2d, ms_d2h;
     double ms_decode, ms_filter, ms_join, ms_count, ms_inflate_gpu, ms_kernels;
     double ms_device;         /* first to last device event of the call on the compute stream (kernels + gaps) */

@@ -34,11 +34,12 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
                 const uint32_t len = v & 0xffffu, nlen = v >> 16;
                 if ((len ^ nlen) != 0xffffu || op_dec + len > out_len) return 3;
                 const uint32_t src_off = br.byte_pos();
-                memcpy(out + op_dec, buf + src_off, len);
+                if ((uint64_t(src_off) + len) * 8 > (uint64_t(in_off) + in_len) * 8) return 3;
                 op_dec += len;
                 br.init(base, src_off + len);
-                q[0] = kTokSkip | len;
-                nq = 1;
+                q[0] = kTokSkip | len;                 // as the kernel: a stored block is a two-slot queue of its own,
+                q[1] = src_off;                        // moved by a copy warp
+                nq = 2;
                 if (last) done = 1;
             } else phase = 1;
         }
@@ -50,6 +51,11 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
             if (br.bit_pos() > (uint64_t(in_off) + in_len) * 8) return 6;      // as the kernel: never more than one round past the end
         }
         // phase 2 emulation
+        if (nq == 2 && !(q[0] >> 31) && (q[0] & kTokSkip)) {
+            memcpy(out + pos_base, buf + q[1], q[0] & 0xffffu);
+            pos_base += q[0] & 0xffffu;
+            nq = 0;
+        }
         for (int base = 0; base < nq; base += 32) {
             uint32_t t[32], len[32], pos[32];
             uint32_t run = 0;

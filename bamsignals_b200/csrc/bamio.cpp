@@ -49,7 +49,11 @@ BamFile::BamFile(const std::string& path) : path_(path) {
     size_ = uint64_t(st.st_size);
     mtime_ns_ = uint64_t(st.st_mtim.tv_sec) * 1000000000ull + uint64_t(st.st_mtim.tv_nsec);
     if (size_ == 0) { ::close(fd_); fd_ = -1; fail(BSG_EOPEN, "Fail to open BAM file " + path); }
-    void* p = mmap(nullptr, size_, PROT_READ, MAP_SHARED, fd_, 0);
+    // A PRIVATE mapping with write permission that nothing ever writes to: the CUDA driver refuses to page-lock a
+    // PROT_READ file mapping (cudaHostRegister: invalid argument, also with cudaHostRegisterReadOnly; probed on the B200
+    // boxes, profiles/r2d_pin_probe_*.txt), and page-locked windows of the mapping are what lets the copy engine read the
+    // compressed bytes straight from the page cache (engine.cu: ensure_pinned).
+    void* p = mmap(nullptr, size_, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd_, 0);
     if (p == MAP_FAILED) { ::close(fd_); fd_ = -1; fail(BSG_EOPEN, "Fail to open BAM file " + path); }
     data_ = static_cast<const uint8_t*>(p);
     try {

@@ -49,6 +49,7 @@ constexpr int64_t kDefaultGpuBatch = 2048ll << 20;   // byte cap of a device-inf
 constexpr size_t kCompChunk = 16u << 20;        // compressed bytes per pinned upload chunk (GPU inflate)
 constexpr uint64_t kSegCBytes = 1ull << 20;     // compressed bytes per fetch segment (parallel walk granularity)
 constexpr uint64_t kSpanGap = 160u << 10;       // file gaps up to this many bytes are uploaded rather than skipped
+constexpr uint64_t kSmallJobBytes = 16u << 20;   // inflated bytes up to which the default path inflates on the host
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
 constexpr int kOutSlots = 3;                    // pinned result-staging ring
@@ -182,51 +183,127 @@ std::unique_ptr<Pool> g_pool;
 std::vector<std::shared_ptr<BamFile>> g_bams;
 
 // ---- direct DMA from the page cache -------------------------------------------------------------------------------------
-// The compressed bytes of a call live in the BAM's read-only file mapping.  Staging them through pinned buffers costs a
-// CPU memcpy of every byte (measured: memcpy + H2D at 17-19 GB/s on 16 host threads, as long as the device inflate).
-// Instead, windows of the mapping are page-locked on first use (cudaHostRegister, read-only, portable) and stay so while
-// the handle is cached: the copy engine then reads the page cache itself.  Where the platform refuses (no read-only
-// registration, a filesystem whose pages cannot be pinned) the staging path is used.
+// The compressed bytes of a call live in the BAM's file mapping.  Staging them through pinned buffers costs a CPU memcpy
+// of every byte and a worker pool that is busy for the whole upload.  Instead, 128 MB windows of the mapping are
+// page-locked (cudaHostRegister, read-only, portable) and the copy engine reads the page cache itself: 55 GB/s, no CPU
+// (profiles/r2d_pin_probe_*.txt).  Page-locking costs ~15 ms per window, so it is kept off the calls: the FIRST call that
+// touches a window stages it as before and only marks it; a background thread locks the marked windows once the call has
+// returned; every later call that needs them finds them locked.  They stay locked while the handle is cached.  Where the
+// platform refuses, the staging path remains.
 constexpr uint64_t kPinWindow = 128ull << 20;
+enum : uint8_t { PIN_NONE = 0, PIN_LOCKED = 1, PIN_WANTED = 2, PIN_BUSY = 3 };
 struct PinnedMapping {
-    std::vector<uint8_t> state;                 // per window: 0 = not tried, 1 = registered
+    std::vector<uint8_t> state;                 // per window
     bool unsupported = false;
 };
 std::mutex g_pin_mu;
+std::condition_variable g_pin_cv;
 std::unordered_map<const BamFile*, PinnedMapping> g_pins;
+std::deque<std::shared_ptr<BamFile>> g_pin_jobs;   // mappings with PIN_WANTED windows
+std::thread g_pin_thread;
+bool g_pin_stop = false;
+int g_pin_dev = 0;
 
-// true when [off, off + len) of the mapping is page-locked (registering the windows it touches if need be)
+// true when [off, off + len) of the mapping is page-locked; windows that are not are marked for the background thread
 bool ensure_pinned(const BamFile& bam, uint64_t off, uint64_t len) {
     if (len == 0) return true;
     std::lock_guard<std::mutex> g(g_pin_mu);
     PinnedMapping& pm = g_pins[&bam];
     if (pm.unsupported) return false;
     const uint64_t nwin = (bam.size() + kPinWindow - 1) / kPinWindow;
-    if (pm.state.size() != nwin) pm.state.assign(nwin, 0);
+    if (pm.state.size() != nwin) pm.state.assign(nwin, PIN_NONE);
+    bool all = true;
     for (uint64_t w = off / kPinWindow; w <= (off + len - 1) / kPinWindow && w < nwin; ++w) {
-        if (pm.state[w]) continue;
-        const uint64_t beg = w * kPinWindow;
-        const uint64_t bytes = ((std::min(bam.size(), beg + kPinWindow) - beg) + 4095) & ~4095ull;     // whole pages of the mapping
-        Nvtx r("bsg:cudaHostRegister window");
-        const cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(bam.data()) + beg, bytes,
-                                               cudaHostRegisterPortable | cudaHostRegisterReadOnly);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            pm.unsupported = true;
-            if (getenv("BSG_DEBUG")) fprintf(stderr, "[bsg] cudaHostRegister of the BAM mapping refused (%s): staging through pinned chunks\n", cudaGetErrorString(e));
-            return false;
-        }
-        pm.state[w] = 1;
+        if (pm.state[w] == PIN_LOCKED) continue;
+        all = false;
+        if (pm.state[w] == PIN_NONE) pm.state[w] = PIN_WANTED;
     }
-    return true;
+    return all;
 }
+
+void pin_thread_main() {
+    cudaSetDevice(g_pin_dev);
+    nvtxNameOsThreadA(uint32_t(syscall(SYS_gettid)), "bsg page-lock");
+    for (;;) {
+        std::shared_ptr<BamFile> bam;
+        {
+            std::unique_lock<std::mutex> lk(g_pin_mu);
+            g_pin_cv.wait(lk, [] { return g_pin_stop || !g_pin_jobs.empty(); });
+            if (g_pin_stop) return;
+            bam = g_pin_jobs.front();
+            g_pin_jobs.pop_front();
+        }
+        for (;;) {
+            uint64_t w = 0;
+            bool found = false;
+            {
+                std::lock_guard<std::mutex> g(g_pin_mu);
+                if (g_pin_stop) break;
+                auto it = g_pins.find(bam.get());
+                if (it == g_pins.end() || it->second.unsupported) break;
+                for (; w < it->second.state.size(); ++w)
+                    if (it->second.state[w] == PIN_WANTED) { it->second.state[w] = PIN_BUSY; found = true; break; }
+            }
+            if (!found) break;
+            const uint64_t beg = w * kPinWindow;
+            const uint64_t bytes = ((std::min(bam->size(), beg + kPinWindow) - beg) + 4095) & ~4095ull;   // whole pages of the mapping
+            nvtxRangePushA("bsg:cudaHostRegister window");
+            const cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(bam->data()) + beg, bytes,
+                                                   cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+            nvtxRangePop();
+            std::lock_guard<std::mutex> g(g_pin_mu);
+            auto it = g_pins.find(bam.get());
+            if (it == g_pins.end()) { if (e == cudaSuccess) cudaHostUnregister(const_cast<uint8_t*>(bam->data()) + beg); break; }
+            if (e == cudaSuccess) it->second.state[w] = PIN_LOCKED;
+            else {
+                cudaGetLastError();
+                it->second.state[w] = PIN_NONE;
+                it->second.unsupported = true;
+                if (getenv("BSG_DEBUG")) fprintf(stderr, "[bsg] cudaHostRegister of the BAM mapping refused (%s): staging through pinned chunks\n", cudaGetErrorString(e));
+            }
+        }
+        bam.reset();                             // may run the handle's deleter (unpin_mapping): no lock is held here
+    }
+}
+
+// after a call: hand the mapping to the background thread if the call marked windows
+void kick_pinning(const std::shared_ptr<BamFile>& bam, int dev) {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    auto it = g_pins.find(bam.get());
+    if (it == g_pins.end() || it->second.unsupported) return;
+    bool wanted = false;
+    for (uint8_t st : it->second.state) wanted = wanted || st == PIN_WANTED;
+    if (!wanted) return;
+    for (auto& j : g_pin_jobs) if (j.get() == bam.get()) return;
+    g_pin_jobs.push_back(bam);
+    if (!g_pin_thread.joinable()) { g_pin_stop = false; g_pin_dev = dev; g_pin_thread = std::thread(pin_thread_main); }
+    g_pin_cv.notify_all();
+}
+
+void stop_pin_thread() {
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        g_pin_stop = true;
+    }
+    g_pin_cv.notify_all();
+    if (g_pin_thread.joinable()) g_pin_thread.join();
+    std::deque<std::shared_ptr<BamFile>> drop;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        drop.swap(g_pin_jobs);
+        g_pin_stop = false;
+    }
+}
+
+// joins the background thread before the globals above are destroyed at process exit (it is defined after them)
+struct PinThreadGuard { ~PinThreadGuard() { stop_pin_thread(); g_bams.clear(); } } g_pin_guard;
 
 void unpin_mapping(const BamFile* bam) {
     std::lock_guard<std::mutex> g(g_pin_mu);
     auto it = g_pins.find(bam);
     if (it == g_pins.end()) return;
     for (size_t w = 0; w < it->second.state.size(); ++w)
-        if (it->second.state[w]) cudaHostUnregister(const_cast<uint8_t*>(bam->data()) + w * kPinWindow);
+        if (it->second.state[w] == PIN_LOCKED) cudaHostUnregister(const_cast<uint8_t*>(bam->data()) + w * kPinWindow);
     cudaGetLastError();
     g_pins.erase(it);
 }
@@ -369,7 +446,14 @@ public:
             segs_.clear();
             plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
         }
-        const bool gpu = opts_.gpu_inflate >= 0;       // 0 = default = device inflate; -1 = host zlib pool
+        // 1 = device inflate, -1 = host zlib pool, 0 = default: device inflate unless the job is tiny.  A device-inflate
+        // launch lasts as long as ONE BGZF block takes a single lane (a few ms) however few blocks there are, and a file
+        // with a handful of index entry points leaves the device record walk a few long serial chains (the reference's
+        // 4.5 MB fixture: 3 entry points, 19 ms per call); the worker pool inflates and walks such a job in well under a
+        // millisecond.
+        uint64_t plan_usize = 0;
+        for (const Segment& sg : segs_) plan_usize += sg.usize;
+        const bool gpu = opts_.gpu_inflate > 0 || (opts_.gpu_inflate == 0 && plan_usize > kSmallJobBytes);
         const int64_t batch_bytes = opts_.batch_bytes > 0 ? opts_.batch_bytes : (gpu ? kDefaultGpuBatch : kDefaultBatch);
         // group segments into batches
         batches_.clear();
@@ -797,6 +881,7 @@ public:
         ctx_->ev_next = 0;
     }
     const bsg_timings& timings() const { return tm_; }
+    void kick_page_locking() { kick_pinning(bamp_, ctx_->dev); }
     void reset_counters() { int nd = tm_.n_devices; int64_t bc = tm_.bytes_compressed, bi = tm_.bytes_inflated, nb = tm_.n_batches;
         memset(&tm_, 0, sizeof tm_); tm_.n_devices = nd; tm_.bytes_compressed = bc; tm_.bytes_inflated = bi; tm_.n_batches = nb; }
 
@@ -1110,12 +1195,14 @@ private:
             bool direct = true;
             for (const CopyPiece& pc : pieces) direct = direct && ensure_pinned(bam_, pc.file_off, pc.len);
             if (direct) {
-                // the copy engine reads the page cache itself: one asynchronous copy per span (cut at 256 MB so that a
-                // long span does not sit in front of the descriptor copies of this batch for longer than it must)
+                // the copy engine reads the page cache itself: one asynchronous copy per span and page-locked window (a
+                // copy must stay inside ONE registered range: across two the driver answers "invalid argument")
                 for (const CopyPiece& pc : pieces)
-                    for (uint64_t o = 0; o < pc.len; o += (256ull << 20)) {
-                        const uint64_t n = std::min<uint64_t>(256ull << 20, pc.len - o);
-                        BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + pc.dst_off + o, bam_.data() + pc.file_off + o, n, cudaMemcpyHostToDevice, c.s_copy));
+                    for (uint64_t o = 0; o < pc.len;) {
+                        const uint64_t f = pc.file_off + o;
+                        const uint64_t n = std::min<uint64_t>((f / kPinWindow + 1) * kPinWindow - f, pc.len - o);
+                        BSG_CUDA(cudaMemcpyAsync(c.g_comp[slot].as<uint8_t>() + pc.dst_off + o, bam_.data() + f, n, cudaMemcpyHostToDevice, c.s_copy));
+                        o += n;
                     }
                 tm_.upload_mode = 1;
             } else {
@@ -1402,6 +1489,7 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
                 s.stage(ext, false);
                 s.finish_count();
                 s.finish_timings(t0);
+                s.kick_page_locking();
                 tms[d] = s.timings();
             } catch (Error& e) { errs[d] = e; }
             catch (std::exception& e) { errs[d] = Error{BSG_EARG, std::string("internal error: ") + e.what()}; }
@@ -1501,6 +1589,7 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
         s.finish_count();
         const double t5 = now_ms();
         s.finish_timings(t0);
+        s.kick_page_locking();
         if (dbg) fprintf(stderr, "[bsg] call host ms: open+regions %.1f, tiles %.1f, begin_count %.1f, stage %.1f, finish_count %.1f\n",
                          t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     });
@@ -1530,6 +1619,7 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
         s.stage(ext, false);
         s.finish_count();
         s.finish_timings(t0);
+        s.kick_page_locking();
     });
 }
 
@@ -1555,6 +1645,7 @@ int bsg_stage_open(bsg_stage** st, const char* bampath, int64_t R, const char* c
         h->s.reset(new Session(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts));
         h->s->stage(ext_hint, true);
         h->s->finish_timings(t0);
+        h->s->kick_page_locking();
         g_stages.push_back(h.get());
         *st = h.release();
     });
@@ -1616,6 +1707,7 @@ int bsg_device_count(void) {
 
 void bsg_shutdown(void) {
     std::lock_guard<std::mutex> g(g_mu);
+    stop_pin_thread();
     for (bsg_stage* st : g_stages) st->s.reset();
     for (auto& c : g_ctx) c.release();
     g_pool.reset();

@@ -34,7 +34,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWsDecWarps = 2;                       // warps whose 32 lanes decode one stream each
 constexpr int kWsStreams = kWsDecWarps * 32;         // streams resident per CTA (= per SM)
-constexpr int kWsCopyWarps = 14;                     // warps that materialise the token queues
+constexpr int kWsCopyWarps = 16;                     // warps that materialise the token queues, four streams each
 constexpr int kWsThreads = (kWsDecWarps + kWsCopyWarps) * 32;
 
 struct WsStream {
@@ -46,10 +46,12 @@ struct WsCtl {
     uint32_t pos[kWsStreams];                        // bytes materialised so far (owned by the stream's copy warp)
     uint32_t out_off[kWsStreams], out_len[kWsStreams];
     uint32_t produced[2][kWsDecWarps];               // did the decode warp hand over anything in round buf?
+    uint32_t bitmap[kWsCopyWarps][32];               // scratch of a copy warp while it builds a token-start bitmap
 };
 constexpr size_t kWsSmem = sizeof(WsStream) * kWsStreams + sizeof(WsCtl);
 static_assert(sizeof(WsStream) % 8 == 0, "stream slots keep the tables aligned");
 static_assert(kWsSmem <= 227 * 1024, "one CTA per SM must fit the opt-in shared memory");
+static_assert(kWsCopyWarps * 4 == kWsStreams, "every copy warp owns four streams");
 
 // fill_queue's table lookups and queue stores through explicit shared-space addresses (kept in registers)
 struct SmemAccess {
@@ -67,107 +69,95 @@ struct SmemAccess {
     __device__ __forceinline__ void put(uint32_t byte_off, uint32_t v) const {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_a + byte_off), "r"(v) : "memory");
     }
-    template <bool DIST> __device__ __forceinline__ uint32_t count(uint32_t len) const {
-        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_count) : offsetof(inflate_core::Tables, lit_count);
+    __device__ __forceinline__ uint32_t sub(uint32_t byte_off) const {
+        constexpr uint32_t off = offsetof(inflate_core::Tables, lit_sub);
+        uint32_t r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + byte_off) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ uint32_t count(uint32_t len) const {
+        constexpr uint32_t off = offsetof(inflate_core::Tables, dist_count);
         uint32_t r;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + 2u * len) : "memory");
         return r;
     }
-    template <bool DIST> __device__ __forceinline__ uint32_t first() const {
-        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_first) : offsetof(inflate_core::Tables, lit_first);
+    __device__ __forceinline__ uint32_t first() const {
+        constexpr uint32_t off = offsetof(inflate_core::Tables, dist_first);
         uint32_t r;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off) : "memory");
         return r;
     }
-    template <bool DIST> __device__ __forceinline__ uint32_t index() const {
-        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_index) : offsetof(inflate_core::Tables, lit_index);
+    __device__ __forceinline__ uint32_t index() const {
+        constexpr uint32_t off = offsetof(inflate_core::Tables, dist_index);
         uint32_t r;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off) : "memory");
         return r;
     }
-    template <bool DIST> __device__ __forceinline__ uint32_t sorted(uint32_t i) const {
-        constexpr uint32_t off = DIST ? offsetof(inflate_core::Tables, dist_sorted) : offsetof(inflate_core::Tables, lit_sorted);
+    __device__ __forceinline__ uint32_t sorted(uint32_t i) const {
+        constexpr uint32_t off = offsetof(inflate_core::Tables, dist_sorted);
         uint32_t r;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + 2u * i) : "memory");
         return r;
     }
 };
 
-// One queue (<= 32 tokens, one per lane) -> bytes behind out[pos_base); returns the new pos_base.
-__device__ __forceinline__ uint32_t materialise(const uint32_t* q, int nq, uint8_t* out, uint32_t pos_base, int lane) {
-    const bool valid = lane < nq;
-    const uint32_t t = valid ? q[lane] : 0u;
-    const bool is_match = (t >> 31) != 0;
-    const uint32_t len = is_match ? (t & 0x1ffu) : (valid ? 1u : 0u);
-    uint32_t incl = len;
+// Copy side: FOUR queues (<= 32 tokens each, one token per lane) -> bytes, interleaved by one warp.
+//
+// Byte-parallel: in every step each lane produces ONE byte of 32 consecutive output bytes of a queue.  The lane finds the
+// token that owns its byte - a bitmap of token start positions (one 32-bit word per 32-byte step, 1024 bytes per
+// window) plus a prefix pop-count, moved between lanes with shuffles - and then where the byte comes from: the token's
+// literal, or `dist` bytes back.  A source in front of the step's 32 bytes is finished output (earlier steps, queues,
+// rounds) and is LOADED; a source inside them (distance < 32: rare) is chased through its own owner token instead; a match
+// that overlaps itself (dist < len) jumps in front of its own start with one modulo.  So the bytes of a step never wait
+// for each other.  A step does wait for the stores of the step before it (a record usually copies from the record in
+// front of it, 40-60 bytes back), and that round trip goes to L2 or - the 64 KiB windows of all resident streams are five
+// times the L2 - to DRAM: the warp therefore works on four queues at once, issuing the loads of all four before it
+// consumes any of them.
+// History (ncu, C2): token-per-lane copies in waves of matches that read each other's output: the copy warps sat on
+// dependent L2 round trips (22 % of all samples on one line) while the decode warps waited at the barrier (42 %), 10.0 ms
+// per wave of 9472 blocks; four bytes per lane chased through the whole window: ~10 rounds of shuffles per step, 10.7 ms;
+// chased through the 128 bytes of the step only: 5.5 rounds, 8.7 ms.
+constexpr int kQpw = 4;                              // queues per copy warp
+
+struct CopyQueue {
+    uint32_t t;                                      // this lane's token
+    int32_t s, e;                                    // it covers bytes [s, e) in u coordinates (byte u lives at al[u])
+    uint32_t bm, pre, firstk;                        // this lane's word of the start bitmap, starts before it, tokens before the window
+    uint8_t* al;                                     // the aligned word at or before the queue's first output byte
+    int32_t a0, end_u;                               // the queue's bytes are [a0, end_u)
+};
+
+// bitmap + prefix of window [wb, wb + 1024) of one queue; bm_s = 32 words of shared memory owned by the calling warp
+__device__ __forceinline__ void copy_window(CopyQueue& Q, int32_t wb, int lane, uint32_t* bm_s) {
+    const bool valid = Q.e > Q.s;
+    const int32_t wend = min(Q.end_u, wb + 1024);
+    // tokens that end at or before the window come first; then bit (start - wb) for every token in the window (a token
+    // that began before the window and reaches into it owns bit 0)
+    Q.firstk = uint32_t(__popc(__ballot_sync(FULL, valid && Q.e <= wb)));
+    bm_s[lane] = 0u;
+    __syncwarp();
+    if (valid && Q.e > wb && Q.s < wend) {
+        const uint32_t r = uint32_t(max(Q.s, wb) - wb);
+        atomicOr(&bm_s[r >> 5], 1u << (r & 31u));
+    }
+    __syncwarp();
+    Q.bm = bm_s[lane];
+    __syncwarp();
+    const uint32_t pc = uint32_t(__popc(Q.bm));
+    uint32_t inc = pc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += up;
+        const uint32_t up = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += up;
     }
-    const uint32_t pos = pos_base + incl - len;
-    if (valid && !is_match) out[pos] = uint8_t(t);
-    // Matches are replayed in WAVES: every pending match of <= 32 bytes whose source bytes all lie before the
-    // first pending token reads only finished output, so all of them are copied at once, each by its own lane
-    // (8-byte pieces: loads first, then stores).  Matches longer than 32 bytes are copied by the whole warp when
-    // they reach the front.
-    uint32_t pending = __ballot_sync(FULL, is_match);
-    const uint32_t own_len = t & 0x1ffu, own_dist = ((t >> 16) & 0x7fffu) + 1u;
-    const bool is_long = is_match && own_len > 32u;
-    const uint32_t src_hi = min(pos, pos - own_dist + own_len);     // end of the bytes a match reads before itself
-    __syncwarp();
-    while (pending) {
-        const int first = __ffs(pending) - 1;
-        const uint32_t front = __shfl_sync(FULL, pos, first);
-        if (__shfl_sync(FULL, uint32_t(is_long), first)) {
-            const uint32_t mt = __shfl_sync(FULL, t, first);
-            const uint32_t mlen = mt & 0x1ffu, mdist = ((mt >> 16) & 0x7fffu) + 1u;
-            uint8_t* dst = out + front;
-            {   // the first 32 bytes never depend on bytes written in this step
-                const int so = (mdist >= 32u || mdist >= mlen) ? int(lane) - int(mdist) : int(uint32_t(lane) % mdist) - int(mdist);
-                dst[lane] = dst[so];
-            }
-            // later steps read one whole period (>= 32 bytes) back: already written, barrier between steps
-            const uint32_t K = mdist >= 32u ? mdist : mdist * (31u / mdist + 1u);
-            for (uint32_t j = 32u + lane; j - lane < mlen; j += 32u) {
-                __syncwarp();
-                if (j < mlen) dst[j] = dst[int(j) - int(K)];
-            }
-            pending &= ~(1u << first);
-            __syncwarp();
-            continue;
-        }
-        const bool ready = ((pending >> lane) & 1u) && !is_long && src_hi <= front;
-        if (ready) {
-            for (uint32_t done = 0; done < own_len; done += 8u) {
-                const uint32_t n = min(own_len - done, 8u);
-                uint8_t* d = out + pos + done;
-                if (pos + done >= 8u) {
-                    // eight source bytes from three aligned words + two funnel shifts (raw is cudaMalloc'ed; the
-                    // bytes around [sp, sp + 8) that the words also cover are finished output or slack)
-                    const uint8_t* sp = d - max(own_dist, 8u);
-                    const uintptr_t sa = reinterpret_cast<uintptr_t>(sp);
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-                    const uint32_t sh = uint32_t(sa & 3u) * 8u;
-                    const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2];
-                    const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                    uint64_t w = uint64_t(lo) | (uint64_t(hi) << 32);
-                    if (own_dist < 8u) {
-                        uint64_t rep = w >> (8u * (8u - own_dist));
-                        for (uint32_t filled = own_dist; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
-                        w = rep;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) if (uint32_t(k) < n) d[k] = uint8_t(w >> (8 * k));
-                } else {
-                    for (uint32_t k = 0; k < n; ++k) d[k] = d[int(k) - int(own_dist)];
-                }
-            }
-        }
-        pending &= ~__ballot_sync(FULL, ready);
-        __syncwarp();
-    }
-    return pos_base + __shfl_sync(FULL, incl, 31);
+    Q.pre = inc - pc;
+}
+
+// owner token of byte xx (window-relative lookup), generic: any lane may ask for any byte of the window
+__device__ __forceinline__ int copy_owner(const CopyQueue& Q, int32_t xx, int32_t wb) {
+    const uint32_t r = uint32_t(xx - wb);
+    const uint32_t m = __shfl_sync(FULL, Q.bm, int(r >> 5)), p = __shfl_sync(FULL, Q.pre, int(r >> 5));
+    return int((Q.firstk + p + uint32_t(__popc(m & ((2u << (r & 31u)) - 1u))) - 1u) & 31u);
 }
 
 __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock* __restrict__ blocks, int n_blocks,
@@ -250,25 +240,98 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                 const bool any = __any_sync(FULL, nq > 0);
                 if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
             } else if (r > 0) {
-                // ---- the queues of the previous round -> bytes ------------------------------------------------------------
+                // ---- the queues of the previous round -> bytes: this warp's four streams, interleaved ----------------------------
                 const int pb = buf ^ 1;
-                for (int k = wid - kWsDecWarps; k < kWsStreams; k += kWsCopyWarps) {
-                    const int nq = int(ctl.qn[pb][k]);
-                    if (nq == 0) continue;                                         // warp-uniform
+                const int cw = wid - kWsDecWarps;
+                uint32_t* bm_s = ctl.bitmap[cw];
+                CopyQueue Q[kQpw];
+                int32_t max_end = 0;
+#pragma unroll
+                for (int j = 0; j < kQpw; ++j) {
+                    const int k = cw * kQpw + j;
+                    int nq = int(ctl.qn[pb][k]);
                     const uint32_t* q = S[k].q[pb];
                     uint8_t* out = raw + ctl.out_off[k];
-                    uint32_t pos = ctl.pos[k];
-                    const uint32_t t0 = q[0];
-                    if (nq == 2 && !(t0 >> 31) && (t0 & kTokSkip)) {               // stored block: copy from the compressed buffer
-                        const uint32_t len = t0 & 0xffffu;
+                    const uint32_t pos = ctl.pos[k];
+                    if (nq == 2 && !(q[0] >> 31) && (q[0] & kTokSkip)) {          // stored block: copy from the compressed buffer
+                        const uint32_t len = q[0] & 0xffffu;
                         const uint8_t* src = comp + q[1];
-                        for (uint32_t j = lane; j < len; j += 32) out[pos + j] = src[j];
-                        pos += len;
-                    } else {
-                        pos = materialise(q, nq, out, pos, lane);
+                        for (uint32_t i = lane; i < len; i += 32) out[pos + i] = src[i];
+                        __syncwarp();
+                        if (lane == 0) ctl.pos[k] = pos + len;
+                        nq = 0;
                     }
-                    __syncwarp();
-                    if (lane == 0) ctl.pos[k] = pos;
+                    const bool valid = lane < nq;
+                    Q[j].t = valid ? q[lane] : 0u;
+                    const uint32_t len = (Q[j].t >> 31) ? (Q[j].t & 0x1ffu) : (valid ? 1u : 0u);
+                    uint32_t incl = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);
+                    uint8_t* first_byte = out + pos;
+                    Q[j].a0 = int32_t(reinterpret_cast<uintptr_t>(first_byte) & 3u);
+                    Q[j].al = first_byte - Q[j].a0;
+                    Q[j].s = int32_t(incl - len) + Q[j].a0;
+                    Q[j].e = Q[j].s + int32_t(len);
+                    Q[j].end_u = total ? Q[j].a0 + int32_t(total) : 0;
+                    Q[j].bm = Q[j].pre = Q[j].firstk = 0u;
+                    max_end = max(max_end, Q[j].end_u);
+                    if (lane == 0 && total) ctl.pos[k] = pos + total;
+                }
+                for (int32_t wb = 0; wb < max_end; wb += 1024) {                   // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < kQpw; ++j)
+                        if (wb < Q[j].end_u) copy_window(Q[j], wb, lane, bm_s);
+                    const int32_t wlim = min(max_end, wb + 1024);
+                    for (int32_t base = wb; base < wlim; base += 32) {
+                        const int32_t x = base + lane;
+                        uint32_t val[kQpw];
+                        int32_t src[kQpw];
+                        uint32_t load_mask = 0u, store_mask = 0u;
+                        // resolve the byte of every queue and issue its load ...
+#pragma unroll
+                        for (int j = 0; j < kQpw; ++j) {
+                            val[j] = 0u; src[j] = 0;
+                            if (base >= Q[j].end_u) continue;                     // warp-uniform
+                            const int32_t lim = max(base, Q[j].a0);              // first byte of the step inside the queue
+                            const bool mine = x >= Q[j].a0 && x < Q[j].end_u;
+                            const uint32_t m = __shfl_sync(FULL, Q[j].bm, (base - wb) >> 5), p = __shfl_sync(FULL, Q[j].pre, (base - wb) >> 5);
+                            const int k = int((Q[j].firstk + p + uint32_t(__popc(m & ((2u << lane) - 1u))) - 1u) & 31u);
+                            uint32_t tk = __shfl_sync(FULL, Q[j].t, k);
+                            int32_t sk = __shfl_sync(FULL, Q[j].s, k);
+                            int32_t xx = x;
+                            bool need = mine;
+                            for (;;) {
+                                if (need) {
+                                    if (!(tk >> 31)) { val[j] = tk & 0xffu; need = false; }
+                                    else {
+                                        const int32_t d = int32_t(((tk >> 16) & 0x7fffu) + 1u);
+                                        int32_t y = xx - d;
+                                        if (y >= sk) y = sk - d + (xx - sk) % d;  // the match overlaps itself: same phase, in front of it
+                                        if (y < lim) { src[j] = y; load_mask |= 1u << j; need = false; }
+                                        else xx = y;
+                                    }
+                                }
+                                if (!__any_sync(FULL, need)) break;
+                                // rare: a source inside this step's 32 bytes: chase it through its own owner token
+                                const int k2 = copy_owner(Q[j], need ? xx : lim, wb);
+                                tk = __shfl_sync(FULL, Q[j].t, k2);
+                                sk = __shfl_sync(FULL, Q[j].s, k2);
+                            }
+                            if (mine) store_mask |= 1u << j;
+                        }
+#pragma unroll
+                        for (int j = 0; j < kQpw; ++j)
+                            if ((load_mask >> j) & 1u) val[j] = Q[j].al[src[j]];
+                        // ... then store them
+#pragma unroll
+                        for (int j = 0; j < kQpw; ++j)
+                            if ((store_mask >> j) & 1u) Q[j].al[x] = uint8_t(val[j]);
+                        __syncwarp();                                              // visible to the next step's loads
+                    }
                 }
             }
             __syncthreads();

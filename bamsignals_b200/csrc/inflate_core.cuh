@@ -2,8 +2,8 @@
 // (tests/host_inflate_harness.cpp compiles this header with a plain C++ compiler).  Everything here is executed by ONE
 // thread per BGZF block: bit reader, decode-table construction, and Huffman symbols -> token queue.
 //
-// Shared-memory budget: 3272 bytes of tables per stream (16-bit entries; the distance table doubles as the code-length
-// scratch while a block header is parsed) + two 32-token queues = 3528 bytes, so that 64 streams fit one SM.
+// Shared-memory budget: 3304 bytes of tables per stream (16-bit entries; the distance table doubles as the code-length
+// scratch while a block header is parsed) + two 32-token queues = 3560 bytes, so that 64 streams fit one SM.
 #pragma once
 #include <cstdint>
 
@@ -28,14 +28,21 @@ constexpr uint32_t kTokMatch = 0x80000000u, kTokSkip = 0x40000000u;
 // 16-bit decode-table entries.
 //   literal/length code:  [3:0] code length, [4] 0 = literal / 1 = anything else,
 //                         literal: [15:8] the byte;  otherwise [7:5] class: 0..5 = length symbol with that many extra
-//                         bits and [15:8] = base length - 3;  7 = end of block;  6 = not decodable from this entry
-//                         (code length 0: the code is longer than the primary table -> canonical slow path;
-//                          code length > 0: invalid symbol 286/287)
+//                         bits and [15:8] = base length - 3;  7 = end of block;  6 = not decodable from this entry:
+//                         [3:0] = 0: no such code (or symbol 286/287): the stream is corrupt;
+//                         [3:0] = b > 0 (primary table only): the code is longer than the primary table - its remaining
+//                         bits index a second-level table of 2^b entries at lit_sub[2 * [15:8]] (entries of the same
+//                         format, [3:0] = the code's full length)
 //   distance code:        [3:0] code length (0 = slow path), [7:4] extra bits, [9:8] mantissa m: base = (m << extra) + 1,
 //                         [10] invalid symbol (30/31)
 // One test of bit 4 separates literals from everything else; one test of the class separates lengths from the rare rest.
 constexpr uint32_t kNonLit = 0x10u, kClsShift = 5, kClsEob = 7u, kClsOther = 6u;
-constexpr uint32_t kLitUnset = kNonLit | (kClsOther << kClsShift);      // length 0: take the slow path
+constexpr uint32_t kLitUnset = kNonLit | (kClsOther << kClsShift);      // class 6, length 0: corrupt stream
+// Second-level entries for literal/length codes of 11-15 bits.  Codes are canonical, so the long codes of a block are
+// sorted by length and share consecutive 10-bit prefixes: every prefix whose codes all have one length needs exactly as
+// many entries as it has codes, and only the (at most four) prefixes in which the length changes waste any - zlib's
+// `enough 288 10 15` gives 1334 entries for both levels, i.e. 310 here.  An overflow is reported as a corrupt block.
+constexpr int kLitSub = 320;
 constexpr uint32_t kDistBad = 0x400u;
 
 BSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -92,11 +99,11 @@ struct BitReader {
 struct Tables {
     uint16_t lit[1 << kLitBits];
     uint16_t dist[1 << kDistBits];
-    uint16_t lit_sorted[288];
+    uint16_t lit_sub[kLitSub];
     uint16_t dist_sorted[32];
-    uint16_t lit_count[16], dist_count[16];
-    // canonical-decode state after the code lengths the primary tables cover (see slow_entry)
-    uint16_t lit_first, lit_index, dist_first, dist_index;
+    uint16_t dist_count[16];
+    // canonical-decode state after the code lengths the primary distance table covers (see slow_entry)
+    uint16_t dist_first, dist_index, pad0, pad1;
 };
 constexpr int kLensBytes = 320;     // code lengths of one block header: 288 literal/length + 32 distance symbols
 static_assert(sizeof(uint16_t) << kDistBits >= kLensBytes, "the distance table doubles as the code-length scratch");
@@ -105,7 +112,7 @@ static_assert(kQueue * 4 >= 32, "the (empty) token queue holds the 32 distance c
 BSG_HD uint32_t lit_entry(int sym, int len) {
     if (sym < 256) return uint32_t(len) | (uint32_t(sym) << 8);
     if (sym == 256) return uint32_t(len) | kNonLit | (kClsEob << kClsShift);
-    if (sym > 285) return uint32_t(len) | kNonLit | (kClsOther << kClsShift);
+    if (sym > 285) return kLitUnset;
     uint32_t eb, base;
     if (sym < 265) { eb = 0; base = uint32_t(sym - 254); }
     else if (sym == 285) { eb = 0; base = 258; }
@@ -126,31 +133,34 @@ struct ArrayAccess {
     const Tables* T;
     uint32_t* q;
     BSG_HD uint32_t lit(uint32_t byte_off) const { return T->lit[byte_off >> 1]; }
+    BSG_HD uint32_t sub(uint32_t byte_off) const { return T->lit_sub[byte_off >> 1]; }
     BSG_HD uint32_t dist(uint32_t byte_off) const { return T->dist[byte_off >> 1]; }
     BSG_HD void put(uint32_t byte_off, uint32_t v) const { q[byte_off >> 2] = v; }
-    template <bool DIST> BSG_HD uint32_t count(uint32_t len) const { return DIST ? T->dist_count[len] : T->lit_count[len]; }
-    template <bool DIST> BSG_HD uint32_t sorted(uint32_t i) const { return DIST ? T->dist_sorted[i] : T->lit_sorted[i]; }
-    template <bool DIST> BSG_HD uint32_t first() const { return DIST ? T->dist_first : T->lit_first; }
-    template <bool DIST> BSG_HD uint32_t index() const { return DIST ? T->dist_index : T->lit_index; }
+    BSG_HD uint32_t count(uint32_t len) const { return T->dist_count[len]; }
+    BSG_HD uint32_t sorted(uint32_t i) const { return T->dist_sorted[i]; }
+    BSG_HD uint32_t first() const { return T->dist_first; }
+    BSG_HD uint32_t index() const { return T->dist_index; }
 };
 
-// Canonical decode of a code longer than the primary table (RFC 1951 3.2.2) from the 32 peeked bits: returns the
-// table entry the symbol would have had (with its real code length), or an "invalid" entry.  The primary lookup has
-// already ruled out every code of up to kLitBits (kDistBits) bits, so the search starts behind them: the (first,
-// index) pair of the canonical walk at that point depends only on the code-length counts and is stored with the
-// tables; most long codes are one or two bits longer than the table, so the loop runs once or twice.
-// Deliberately NOT inlined into the hot loop on the device: about one token in twenty comes here, and the loop body
-// must stay small for the instruction cache (measured: 4 % of the kernel's stall samples were instruction fetches).
-template <bool DIST, class A>
+// Canonical decode of a DISTANCE code longer than the primary table (RFC 1951 3.2.2) from the 32 peeked bits: returns
+// the table entry the symbol would have had (with its real code length), or an "invalid" entry.  The primary lookup has
+// already ruled out every code of up to kDistBits bits, so the search starts behind them: the (first, index) pair of the
+// canonical walk at that point depends only on the code-length counts and is stored with the tables.  Fewer than one
+// match in a hundred comes here (literal/length codes, one token in twenty, have their second-level table instead).
+// Deliberately NOT inlined into the hot loop on the device.
+template <class A>
 #if defined(__CUDA_ARCH__)
 __device__ __noinline__
 #else
 inline
 #endif
 uint32_t slow_entry(uint32_t v, const A& acc) {
-    constexpr int kBits = DIST ? kDistBits : kLitBits;
+    constexpr int kBits = kDistBits;
+#if defined(BSG_SLOW_COUNTER) && !defined(__CUDA_ARCH__)
+    ++BSG_SLOW_COUNTER[1];                        // host-side statistics only (tools / tests)
+#endif
     int code = int(rev_bits(v & ((1u << kBits) - 1u), kBits)) << 1;       // the first kBits bits, MSB first
-    int first = int(acc.template first<DIST>()), index = int(acc.template index<DIST>());
+    int first = int(acc.first()), index = int(acc.index());
     v >>= kBits;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -158,17 +168,17 @@ uint32_t slow_entry(uint32_t v, const A& acc) {
     for (int len = kBits + 1; len <= 15; ++len) {
         code |= int(v & 1u);
         v >>= 1;
-        const int c = int(acc.template count<DIST>(uint32_t(len)));
+        const int c = int(acc.count(uint32_t(len)));
         if (code - c < first) {
-            const int sym = int(acc.template sorted<DIST>(uint32_t(index + (code - first))));
-            return DIST ? dist_entry(sym, len) : lit_entry(sym, len);
+            const int sym = int(acc.sorted(uint32_t(index + (code - first))));
+            return dist_entry(sym, len);
         }
         index += c;
         first += c;
         first <<= 1;
         code <<= 1;
     }
-    return DIST ? (15u | kDistBad) : (15u | kNonLit | (kClsOther << kClsShift));
+    return 15u | kDistBad;
 }
 
 // Serial table construction by the owning thread.  is_dist selects the entry format.  Returns false when the code
@@ -203,6 +213,67 @@ BSG_HD bool build_table(const uint8_t* lens, int n, uint16_t* primary, int bits,
         }
     }
     return ok != 0;
+}
+
+// Literal/length tables of one block: 10-bit primary table + second-level tables for the longer codes.
+// Returns false when the code is over-subscribed or (corrupt input only) the second level overflows.
+BSG_HD bool build_lit_table(const uint8_t* lens, Tables& T) {
+    constexpr int n = 288, kRoot = kLitBits;
+    for (int i = 0; i < (1 << kRoot); ++i) T.lit[i] = uint16_t(kLitUnset);
+    int cnt[16];
+    for (int l = 0; l < 16; ++l) cnt[l] = 0;
+    for (int s = 0; s < n; ++s) cnt[lens[s] & 15]++;
+    cnt[0] = 0;
+    int left = 1, ok = 1;
+    for (int l = 1; l <= 15; ++l) { left = left * 2 - cnt[l]; if (left < 0) { ok = 0; left = 0; } }    // over-subscribed
+    if (!ok) return false;
+    int first_code[16], next[16];
+    first_code[0] = 0; first_code[1] = 0;
+    for (int l = 1; l < 15; ++l) first_code[l + 1] = (first_code[l] + cnt[l]) << 1;
+    for (int l = 0; l < 16; ++l) next[l] = first_code[l];
+    // pass 1: short codes fill the primary table; a long code leaves the number of second-level bits its prefix needs
+    int pmin = 1 << kRoot;
+    for (int s = 0; s < n; ++s) {
+        const int l = lens[s] & 15;
+        if (!l) continue;
+        const uint32_t code = uint32_t(next[l]++);
+        if (l <= kRoot) {
+            const uint16_t e = uint16_t(lit_entry(s, l));
+            for (int k = int(rev_bits(code, uint32_t(l))); k < (1 << kRoot); k += (1 << l)) T.lit[k] = e;
+        } else {
+            const int pre = int(code >> (l - kRoot));                 // the code's first 10 bits, MSB first
+            uint16_t& slot = T.lit[rev_bits(uint32_t(pre), kRoot)];
+            if (uint32_t(l - kRoot) > (slot & 15u)) slot = uint16_t(kLitUnset | uint32_t(l - kRoot));
+            if (pre < pmin) pmin = pre;
+        }
+    }
+    if (pmin == (1 << kRoot)) return true;                            // no long codes
+    // pass 2: long codes own the top of the code space: give every prefix from pmin up its second-level table
+    int off = 0;
+    for (int pre = pmin; pre < (1 << kRoot); ++pre) {
+        uint16_t& slot = T.lit[rev_bits(uint32_t(pre), kRoot)];
+        const uint32_t e = slot;
+        if ((e & (kNonLit | (7u << kClsShift))) != kLitUnset || !(e & 15u)) continue;    // a short code, or nothing at all
+        const int bits = int(e & 15u), size = 1 << bits;
+        if (off + size > kLitSub) return false;
+        slot = uint16_t(kLitUnset | uint32_t(bits) | (uint32_t(off >> 1) << 8));
+        for (int j = 0; j < size; ++j) T.lit_sub[off + j] = uint16_t(kLitUnset);
+        off += size;
+    }
+    // pass 3: the long codes themselves
+    for (int l = 0; l < 16; ++l) next[l] = first_code[l];
+    for (int s = 0; s < n; ++s) {
+        const int l = lens[s] & 15;
+        if (!l) continue;
+        const uint32_t code = uint32_t(next[l]++);
+        if (l <= kRoot) continue;
+        const int rest = l - kRoot;
+        const uint32_t link = T.lit[rev_bits(code >> rest, kRoot)];
+        const int bits = int(link & 15u), base = int(link >> 8) * 2;
+        const uint16_t e = uint16_t(lit_entry(s, l));
+        for (int k = int(rev_bits(code & ((1u << rest) - 1u), uint32_t(rest))); k < (1 << bits); k += (1 << rest)) T.lit_sub[base + k] = e;
+    }
+    return true;
 }
 
 // Block header: reads BFINAL/BTYPE and, for Huffman blocks, the code lengths, then builds the tables.
@@ -268,7 +339,7 @@ BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* dlens, int* last) {
         for (int k = nlit; k < 288; ++k) lens[k] = 0;
     }
     for (int k = 0; k < 32; ++k) dlens[k] = lens[288 + k];
-    bool ok = build_table(lens, 288, T.lit, kLitBits, T.lit_count, T.lit_sorted, false, &T.lit_first, &T.lit_index);
+    bool ok = build_lit_table(lens, T);
     ok = build_table(dlens, ndist, T.dist, kDistBits, T.dist_count, T.dist_sorted, true, &T.dist_first, &T.dist_index) && ok;
     return ok ? 0 : 2;
 }
@@ -295,9 +366,11 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
             continue;
         }
         uint32_t cls = (e >> kClsShift) & 7u;
-        if (cls >= kClsOther) {                       // rare: end of block, a code longer than the primary table, garbage
-            if (!(e & 15u)) {
-                e = slow_entry<false>(v, acc);
+        if (cls >= kClsOther) {                       // end of block, a code longer than the primary table, garbage
+            if (cls == kClsOther) {
+                const uint32_t sb = e & 15u;
+                if (!sb) { err = 1; break; }
+                e = acc.sub((e >> 8) * 4u + (((v >> kLitBits) & ~(~0u << sb)) << 1));      // second level: one more lookup
                 cls = (e >> kClsShift) & 7u;
                 if (!(e & kNonLit)) {
                     acc.put(qo, e >> 8);
@@ -305,10 +378,11 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
                     qo += 4; ++op;
                     continue;
                 }
+                if (cls == kClsOther) { err = 1; break; }
             }
-            if (cls >= kClsOther) {
+            if (cls == kClsEob) {
                 br.consume_short(e & 15u);
-                if (cls == kClsEob) *eob = 1; else err = 1;
+                *eob = 1;
                 break;
             }
         }
@@ -316,7 +390,7 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
         const uint32_t mlen = (e >> 8) + 3u + ((v >> len) & ~(~0u << cls));
         const uint32_t v2 = funnel_r(v, br.peek_hi(), used);      // used <= 20
         uint32_t d = acc.dist((v2 << 1) & kDistMask2);
-        if (!(d & 15u)) d = slow_entry<true>(v2, acc);
+        if (!(d & 15u)) d = slow_entry(v2, acc);
         const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
         uint32_t mdist = (((d >> 8) & 3u) << deb) + 1u + ((v2 >> dl) & ~(~0u << deb));
         br.consume(used + dl + deb);                               // <= 48

@@ -70,8 +70,10 @@ typedef struct bsg_opts {
                                  -1 = off */
     int32_t use_cache;        /* reserved, must be 0 (open BAM handles and buffers are always reused across calls;
                                  record data is never cached: every call reads, inflates and decodes the file again) */
-    int32_t gpu_inflate;      /* 0 (default) or 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the
-                                 device (the host only ships compressed bytes); -1: host zlib worker pool */
+    int32_t gpu_inflate;      /* 1: inflate BGZF blocks + verify CRC32 + walk record boundaries on the device (the host
+                                 only ships compressed bytes); -1: host zlib worker pool; 0 (default): on the device
+                                 unless the job inflates to less than 16 MiB, which the worker pool finishes sooner than
+                                 one device launch */
     int32_t stream_min_ints;  /* result ints that must be final before a portion is counted + shipped while later
                                  batches are still inflating; 0 = default (4 Mi), -1 = never (one pass at the end) */
     int32_t reserved[7];

@@ -56,73 +56,63 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
             pos_base += q[0] & 0xffffu;
             nq = 0;
         }
-        for (int base = 0; base < nq; base += 32) {
-            uint32_t t[32], len[32], pos[32];
+        if (nq > 0) {
+            // the kernel's byte-parallel materialisation (inflate.cu: materialise), lane by lane: token starts in a
+            // bitmap (1024-byte windows), owner of a byte = prefix pop-count, sources inside the window are chased
+            // through their owner tokens, sources before it are read from finished output
+            uint32_t t[32], incl[32]; int32_t s[32], e[32];
             uint32_t run = 0;
             for (int lane = 0; lane < 32; ++lane) {
-                const bool valid = base + lane < nq;
-                t[lane] = valid ? q[base + lane] : 0;
-                const bool m = valid && (t[lane] >> 31), sk = valid && !m && (t[lane] & kTokSkip);
-                len[lane] = !valid ? 0 : (m ? (t[lane] & 0x1ffu) : (sk ? (t[lane] & 0xffffffu) : 1u));
-                pos[lane] = pos_base + run;
-                run += len[lane];
-                if (valid && !m && !sk) out[pos[lane]] = uint8_t(t[lane]);
+                const bool valid = lane < nq;
+                t[lane] = valid ? q[lane] : 0;
+                const uint32_t len = !valid ? 0 : ((t[lane] >> 31) ? (t[lane] & 0x1ffu) : 1u);
+                run += len; incl[lane] = run;
             }
-            // waves, exactly as k_inflate_q2 replays them
-            uint32_t pending = 0;
-            for (int k = 0; k < 32; ++k) if (base + k < nq && (t[k] >> 31)) pending |= 1u << k;
-            while (pending) {
-                const int first = __builtin_ctz(pending);
-                const uint32_t front = pos[first];
-                const uint32_t flen = t[first] & 0x1ffu;
-                if (flen > 32u) {
-                    const uint32_t mlen = flen, mdist = ((t[first] >> 16) & 0x7fffu) + 1u, mpos = front;
-                    const uint32_t K = mdist >= 32 ? mdist : mdist * (31u / mdist + 1u);
-                    for (uint32_t s0 = 0; s0 < mlen; s0 += 32) {
-                        uint8_t tmp[32];
-                        for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) {     // all loads of the step ...
-                            const uint32_t j = s0 + lane;
-                            if (s0 == 0) tmp[lane] = (mdist >= 32 || mdist >= mlen) ? out[mpos + j - mdist] : out[mpos - mdist + (j % mdist)];
-                            else tmp[lane] = out[mpos + j - K];
-                        }
-                        for (uint32_t lane = 0; lane < 32 && s0 + lane < mlen; ++lane) out[mpos + s0 + lane] = tmp[lane];   // ... then all stores
-                    }
-                    pending &= ~(1u << first);
-                    continue;
-                }
-                uint32_t ready = 0;
-                for (int k = 0; k < 32; ++k) {
-                    if (!((pending >> k) & 1u)) continue;
-                    const uint32_t ol = t[k] & 0x1ffu, od = ((t[k] >> 16) & 0x7fffu) + 1u;
-                    const uint32_t src_hi = pos[k] < pos[k] - od + ol ? pos[k] : pos[k] - od + ol;
-                    if (ol <= 32u && src_hi <= front) ready |= 1u << k;
-                }
-                // Ready lanes run concurrently on the GPU, so they must not depend on each other: replay them in REVERSE
-                // token order here - a lane that read bytes another ready lane has yet to write would break the CRC.
-                for (int k = 31; k >= 0; --k) {
-                    if (!((ready >> k) & 1u)) continue;
-                    const uint32_t ol = t[k] & 0x1ffu, od = ((t[k] >> 16) & 0x7fffu) + 1u;
-                    for (uint32_t done = 0; done < ol; done += 8) {
-                        const uint32_t n = ol - done < 8 ? ol - done : 8;
-                        uint8_t* d = out + pos[k] + done;
-                        if (pos[k] + done >= 8) {
-                            const uint8_t* sp = d - (od > 8 ? od : 8);
-                            uint64_t w = 0;
-                            for (int q = 0; q < 8; ++q) w |= uint64_t(sp[q]) << (8 * q);
-                            if (od < 8) {
-                                uint64_t rep = w >> (8u * (8u - od));
-                                for (uint32_t filled = od; filled < 8u; filled <<= 1) rep |= rep << (8u * filled);
-                                w = rep;
-                            }
-                            for (uint32_t q = 0; q < n; ++q) d[q] = uint8_t(w >> (8 * q));
-                        } else {
-                            for (uint32_t q = 0; q < n; ++q) d[q] = d[int(q) - int(od)];
-                        }
+            const uint32_t total = run;
+            uint8_t* first_byte = out + pos_base;
+            const uint32_t a0 = uint32_t(reinterpret_cast<uintptr_t>(first_byte) & 3u);
+            uint8_t* al = first_byte - a0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const uint32_t len = lane < nq ? ((t[lane] >> 31) ? (t[lane] & 0x1ffu) : 1u) : 0u;
+                s[lane] = int32_t(incl[lane] - len + a0); e[lane] = s[lane] + int32_t(len);
+            }
+            const int32_t end_u = int32_t(a0 + total);
+            for (int32_t wb = 0; wb < end_u; wb += 1024) {
+                const int32_t wend = std::min(end_u, wb + 1024);
+                uint32_t firstk = 0, bm[32], pre[32];
+                for (int k = 0; k < 32; ++k) bm[k] = 0;
+                for (int lane = 0; lane < 32; ++lane) {
+                    const bool valid = lane < nq;
+                    if (valid && e[lane] <= wb) ++firstk;
+                    if (valid && e[lane] > wb && s[lane] < wend) {
+                        const uint32_t r = uint32_t(std::max(s[lane], wb) - wb);
+                        bm[r >> 5] |= 1u << (r & 31u);
                     }
                 }
-                pending &= ~ready;
+                uint32_t acc = 0;
+                for (int k = 0; k < 32; ++k) { pre[k] = acc; acc += uint32_t(__builtin_popcount(bm[k])); }
+                for (int32_t base = wb; base < wend; base += 32) {      // one warp step: all its loads precede its stores
+                    const int32_t lim = std::max(base, int32_t(a0)), bend = std::min(wend, base + 32);
+                    uint8_t stage[128];
+                    for (int32_t u = lim; u < bend; ++u) {
+                        int32_t xx = u;
+                        for (int hops = 0;; ++hops) {
+                            if (hops > 40) return 7;
+                            const uint32_t r = uint32_t(xx - wb);
+                            const int k = int((firstk + pre[r >> 5] + uint32_t(__builtin_popcount(bm[r >> 5] & ((2u << (r & 31u)) - 1u))) - 1u) & 31u);
+                            if (!(xx >= s[k] && xx < e[k])) return 8;  // the owner lookup must land on the covering token
+                            if (!(t[k] >> 31)) { stage[u - base] = uint8_t(t[k]); break; }
+                            const int32_t d = int32_t(((t[k] >> 16) & 0x7fffu) + 1u);
+                            int32_t y = xx - d;
+                            if (y >= s[k]) y = s[k] - d + (xx - s[k]) % d;
+                            if (y < lim) { stage[u - base] = al[y]; break; }
+                            xx = y;
+                        }
+                    }
+                    for (int32_t u = lim; u < bend; ++u) al[u] = stage[u - base];
+                }
             }
-            pos_base += run;
+            pos_base += total;
         }
         if (done) break;
     }

@@ -57,7 +57,9 @@ def test_config1_bamcount_100x1kb(fixture_bam):
     got = B.bamCount(fixture_bam, gr, mapqual=0, ss=False)
     assert got.shape == (100,) and np.array_equal(got, O.bamCount(fixture_bam, gr, mapqual=0, ss=False))
     t = B.timings()
-    assert t["records"] > 0 and t["n_launches"] >= 4
+    assert t["records"] > 0 and t["n_launches"] >= 3                      # decode + filter, join, count (a tiny job inflates on the host)
+    got = B.bamCount(fixture_bam, gr, mapqual=0, ss=False, opts=B.default_opts(gpu_inflate=1))
+    assert np.array_equal(got, O.bamCount(fixture_bam, gr, mapqual=0, ss=False)) and B.timings()["n_launches"] >= 7
 
 
 @pytest.mark.parametrize("binsize", [2, 3, 20, 200, 5000])

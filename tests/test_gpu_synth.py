@@ -241,7 +241,7 @@ def test_streaming_finalisation_small_batches(gen_dir, preset, gs, stream):
     gr, kw, fn = WL.regions(preset, gs)
     want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
     for batch in (1 << 16, 1 << 19):
-        got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch, stream_min_ints=stream), **kw)
+        got = getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch, stream_min_ints=stream, gpu_inflate=1), **kw)
         t = B.timings()
         assert np.array_equal(WL.as_flat(got), want)
         if stream > 0 and batch == (1 << 16):
@@ -259,7 +259,7 @@ def test_streaming_with_shuffled_and_overlapping_regions(gen_dir):
     start[::7] = start[0]
     width[::7] = width[0]
     gr = B.GRanges(["chr1"] * n, start, width, rng.choice(["+", "-", "*"], n).tolist())
-    o = B.default_opts(batch_bytes=1 << 17, stream_min_ints=1)
+    o = B.default_opts(batch_bytes=1 << 17, stream_min_ints=1, gpu_inflate=1)
     same(B.bamCoverage(bam, gr, paired_end="extend", opts=o).as_list(), O.bamCoverage(bam, gr, paired_end="extend", nthreads=8).as_list())
     same(B.bamProfile(bam, gr, binsize=3, ss=True, shift=40, opts=o).as_list(), O.bamProfile(bam, gr, binsize=3, ss=True, shift=40, nthreads=8).as_list())
     assert np.array_equal(B.bamCount(bam, gr, ss=True, paired_end="midpoint", opts=o), O.bamCount(bam, gr, ss=True, paired_end="midpoint", nthreads=8))

@@ -56,8 +56,8 @@ def test_gpu_matches_oracle_and_spec(tmp_path, seed):
     bam = RC.write(sc, str(tmp_path / "r.bam"))
     want = _call(O, sc, bam)
     assert np.array_equal(want, RC.spec_counts(sc))
-    variants = [B.default_opts(), B.default_opts(gpu_inflate=-1),
-                B.default_opts(stream_min_ints=1, batch_bytes=1 << 16),
+    variants = [B.default_opts(gpu_inflate=1), B.default_opts(gpu_inflate=-1),
+                B.default_opts(gpu_inflate=1, stream_min_ints=1, batch_bytes=1 << 16),
                 B.default_opts(gpu_inflate=-1, stream_min_ints=1, batch_bytes=1 << 14, inflate_threads=2)]
     for k, o in enumerate(variants):
         got = _call(B, sc, bam, opts=o)

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         }
 #pragma unroll
                         for (int j = 0; j < kQpw; ++j)
-                            if ((load_mask >> j) & 1u) val[j] = Q[j].al[src[j]];
+                            if ((load_mask >> j) & 1u) val[j] = __ldcg(Q[j].al + src[j]);     // L2 only: L1 stays with the decode lanes
                         // ... then store them
 #pragma unroll
                         for (int j = 0; j < kQpw; ++j)

@@ -70,31 +70,48 @@ struct BitReader {
     const uint32_t* base;  // the buffer (uniform for all blocks of a launch)
     uint32_t wi;           // index of the next word to load
     uint32_t w0, w1, w2, bo;
+    // One lane per stream reads its compressed bytes word by word.  L1 is filled by 32-byte SECTOR: the sector a word
+    // lives in serves eight refills of that lane if it stays in L1 (the copy warps' loads bypass L1 for that reason), and
+    // the sector two ahead is requested whenever the reader enters a sector, ~35 tokens before its first word is needed.
+    // (ncu before this: a third of the decode warps' time was the refill waiting for its word from L2 / DRAM - a shifting
+    // register window cannot look further ahead than one refill, the move of the pending word waits for it.)
+    BSG_HD void next_sector() const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 16u));
+#endif
+    }
     BSG_HD void init(const uint32_t* buf, uint32_t byte_off) {
         base = buf;
         wi = byte_off >> 2;
         bo = (byte_off & 3u) * 8u;
         w0 = base[wi]; w1 = base[wi + 1]; w2 = base[wi + 2];
         wi += 3;
+#if defined(__CUDA_ARCH__)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 8u));
+#endif
+        next_sector();
     }
     BSG_HD uint32_t peek() const { return funnel_r(w0, w1, bo); }           // next 32 bits
     BSG_HD uint32_t peek_hi() const { return funnel_r(w1, w2, bo); }        // the 32 bits after those
+    BSG_HD void refill() {
+        bo -= 32; w0 = w1; w1 = w2; w2 = base[wi];
+        if ((wi & 7u) == 0u) next_sector();
+        ++wi;
+    }
     BSG_HD void consume_short(uint32_t n) {                                   // n <= 32
         bo += n;
-        if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
+        if (bo >= 32) refill();
     }
     BSG_HD void consume(uint32_t n) {                                         // n <= 64
         bo += n;
         if (bo >= 32) {
-            bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++];
-            if (bo >= 32) { bo -= 32; w0 = w1; w1 = w2; w2 = base[wi++]; }
+            refill();
+            if (bo >= 32) refill();
         }
     }
     BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 32u + bo; }  // bits from the start of the buffer
     BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 4u + (bo >> 3); }   // only valid when bo is a multiple of 8
 };
-// (Measured and dropped in round 2, profiles/r2_ab_inflate_variants_*.json: prefetching the next 128-byte line of
-// compressed input into L1 / L2 whenever the reader enters a line: 72.9 / 72.5 vs 73.7 ms on C2, within noise.)
 
 struct Tables {
     uint16_t lit[1 << kLitBits];
@@ -344,14 +361,19 @@ BSG_HD int read_block_header(BR& br, Tables& T, uint8_t* dlens, int* last) {
     return ok ? 0 : 2;
 }
 
-// Phase 1: decode symbols into the queue until it holds kQueue tokens or the block ends.
+// Decode symbols into the queue until it holds kQueue tokens or the block ends.
 // *op_dec = bytes decoded so far (updated).  Returns the number of tokens; *eob is set at end-of-block; *bad is
 // sticky (errors do not stop the loop: every access stays in bounds, the caller discards the round).
 // A match is decoded from ONE 64-bit look-ahead (length code + extra bits <= 20 bits, distance code + extra bits
 // <= 28 bits) and consumed once.
+// Literals and matches run through ONE instruction sequence (a literal is a "match" with no extra bits whose distance
+// lookup is thrown away): on the device 32 lanes decode 32 streams in lock step, and a warp that branched on
+// literal / match would execute both sides one after the other in nearly every step.  Only the rare cases branch: codes
+// longer than the primary table (second-level lookup), distance codes longer than theirs, end of block, garbage.
 template <class BR, class A>
 BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad) {
     constexpr uint32_t kLitMask2 = ((1u << kLitBits) - 1u) << 1, kDistMask2 = ((1u << kDistBits) - 1u) << 1;
+    constexpr uint32_t kClassMask = kNonLit | (7u << kClsShift);
     uint32_t qo = 0;                  // byte offset of the next queue slot
     uint32_t op = *op_dec;
     int err = 0;
@@ -359,44 +381,28 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
     do {
         const uint32_t v = br.peek();
         uint32_t e = acc.lit((v << 1) & kLitMask2);
-        if (!(e & kNonLit)) {                         // literal with a short code: the common non-match case
-            acc.put(qo, e >> 8);
-            br.consume_short(e & 15u);
-            qo += 4; ++op;
-            continue;
+        if ((e & kClassMask) == kLitUnset) {          // a code longer than the primary table, or no code at all
+            const uint32_t sb = e & 15u;
+            if (!sb) { err = 1; break; }
+            e = acc.sub((e >> 8) * 4u + (((v >> kLitBits) & ~(~0u << sb)) << 1));      // second level: one more lookup
         }
-        uint32_t cls = (e >> kClsShift) & 7u;
-        if (cls >= kClsOther) {                       // end of block, a code longer than the primary table, garbage
-            if (cls == kClsOther) {
-                const uint32_t sb = e & 15u;
-                if (!sb) { err = 1; break; }
-                e = acc.sub((e >> 8) * 4u + (((v >> kLitBits) & ~(~0u << sb)) << 1));      // second level: one more lookup
-                cls = (e >> kClsShift) & 7u;
-                if (!(e & kNonLit)) {
-                    acc.put(qo, e >> 8);
-                    br.consume_short(e & 15u);
-                    qo += 4; ++op;
-                    continue;
-                }
-                if (cls == kClsOther) { err = 1; break; }
-            }
-            if (cls == kClsEob) {
-                br.consume_short(e & 15u);
-                *eob = 1;
-                break;
-            }
+        const bool is_lit = !(e & kNonLit);
+        const uint32_t cls = (e >> kClsShift) & 7u;
+        if (!is_lit && cls >= kClsOther) {            // end of block, or garbage
+            if (cls == kClsEob) { br.consume_short(e & 15u); *eob = 1; } else err = 1;
+            break;
         }
-        const uint32_t len = e & 15u, used = len + cls;            // cls = number of extra bits
-        const uint32_t mlen = (e >> 8) + 3u + ((v >> len) & ~(~0u << cls));
+        const uint32_t len = e & 15u, eb = is_lit ? 0u : cls, used = len + eb;      // eb = number of extra bits
+        const uint32_t mlen = (e >> 8) + 3u + ((v >> len) & ~(~0u << eb));
         const uint32_t v2 = funnel_r(v, br.peek_hi(), used);      // used <= 20
         uint32_t d = acc.dist((v2 << 1) & kDistMask2);
-        if (!(d & 15u)) d = slow_entry(v2, acc);
+        if (!is_lit && !(d & 15u)) d = slow_entry(v2, acc);
         const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
         uint32_t mdist = (((d >> 8) & 3u) << deb) + 1u + ((v2 >> dl) & ~(~0u << deb));
-        br.consume(used + dl + deb);                               // <= 48
-        if ((d & kDistBad) != 0u || mdist > op) { err = 1; mdist = 1; }
-        acc.put(qo, kTokMatch | ((mdist - 1u) << 16) | mlen);
-        qo += 4; op += mlen;
+        br.consume(is_lit ? len : used + dl + deb);                // <= 48
+        if (!is_lit && ((d & kDistBad) != 0u || mdist > op)) { err = 1; mdist = 1; }
+        acc.put(qo, is_lit ? (e >> 8) : (kTokMatch | ((mdist - 1u) << 16) | mlen));
+        qo += 4; op += is_lit ? 1u : mlen;
     } while (qo < uint32_t(kQueue) * 4u);
     *op_dec = op;
     *bad |= err;

@@ -31,7 +31,8 @@ __device__ __forceinline__ int warp_sum(int v) {
 // Fixed part of a record (offsets from the block_size field): refID +4, pos +8, l_read_name +12, mapq +13,
 // bin +14, n_cigar_op +16, flag +18, l_seq +20, next_refID +24, next_pos +28, tlen +32, read_name +36, cigar after.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSpanCap = 24 * 1024;   // bytes of shared staging per CTA (average record <= 96 B)
+constexpr int kDecThreads = kDecodeChunk;
+constexpr int kSpanCap = 96 * kDecThreads;   // bytes of shared staging per CTA (average record <= 96 B)
 
 struct GlobalLd {
     const uint8_t* raw;
@@ -110,13 +111,13 @@ __device__ __forceinline__ bool keep_read(const FilterParams& p, uint32_t fm, in
 // (tid, pos for the join; c0, c1 for the counting kernels) instead of a 20-byte table row written, read again and
 // turned into 8 more bytes by a second kernel.
 template <bool COVERAGE>
-__global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const DecodeBatch* __restrict__ table,
+__global__ void __launch_bounds__(kDecThreads) k_decode(DecodeBatch single, const DecodeBatch* __restrict__ table,
                                                      int n_batches, ReadTable t, FilterParams p, DeviceScalars* sc) {
     extern __shared__ __align__(128) uint8_t sm_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_lo, s_bytes;
     __shared__ int s_hlo, s_hhi, s_ghlo, s_ghhi;
-    __shared__ int2 s_last[kThreads / 32];         // (tid, pos) of every warp's last record
+    __shared__ int2 s_last[kDecThreads / 32];         // (tid, pos) of every warp's last record
     // which batch does this chunk belong to?
     DecodeBatch B = single;
     int bi = 0;
@@ -129,11 +130,11 @@ __global__ void __launch_bounds__(kThreads) k_decode(DecodeBatch single, const D
         B = table[lo];
         bi = lo;
     }
-    const int i0 = (int(blockIdx.x) - B.chunk0) * kThreads;
+    const int i0 = (int(blockIdx.x) - B.chunk0) * kDecThreads;
     const int i = i0 + threadIdx.x;
     const bool active = i < B.n;
     if (threadIdx.x == 0) {
-        const int i1 = min(i0 + kThreads, B.n);
+        const int i1 = min(i0 + kDecThreads, B.n);
         const uint32_t o_lo = B.offs[i0], o_hi = B.offs[i1];
         const uint32_t lo = o_lo & ~15u;
         const uint32_t bytes = (o_hi - lo + 15u) & ~15u;
@@ -447,15 +448,19 @@ __global__ void __launch_bounds__(kThreads) k_profile_agg(TileTable tiles, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K5 bamCoverage: one CTA per tile; +1/-1 into a shared difference array, then a block-wide inclusive scan
-// (4 ints per thread, warp shuffles, one carry per 1024-element chunk) done in place, then the coalesced write-out.
-// A tile is treated as its own region: the clamp max(start - loc, 0) makes every tile's scan self-contained.
+// K5 bamCoverage: one CTA per tile; +1/-1 into a shared difference array, then a block-wide inclusive scan fused with
+// the coalesced write-out.  A tile is treated as its own region: the clamp max(start - loc, 0) makes every tile's scan
+// self-contained.
+// The scan: every WARP owns one contiguous eighth of the tile and runs through it 128 ints at a time (one int4 per
+// lane, warp shuffles, its own running carry in a register), leaving its total in shared memory; after ONE barrier every
+// warp adds the totals of the warps before it while it streams its own part out.  (Round 1 scanned 1024-int chunks
+// across the whole CTA with three barriers per chunk: ncu showed the kernel issue-bound - 66 % of the issue slots, 2.5 TB/s
+// of DRAM traffic - on ~6 k warp instructions per tile, half of them the scan.)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const int32_t* __restrict__ c0,
                                                        const int32_t* __restrict__ c1, int32_t* __restrict__ out) {
     extern __shared__ __align__(16) int32_t smem[];
     __shared__ int32_t s_warp[kThreads / 32];
-    __shared__ int32_t s_carry;
     const int64_t tix = blockIdx.x;
     const int32_t loc = tiles.loc[tix], len = tiles.len[tix];
     const bool neg_region = tiles.strand[tix] < 0;
@@ -467,9 +472,9 @@ __global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const in
     const int ph = int(off & 3);
     int32_t* d = smem + ph;
     const int total = ph + len;
-    const int padded = (total + 3) & ~3;
-    for (int k = threadIdx.x; k < padded; k += kThreads) smem[k] = 0;
-    if (threadIdx.x == 0) s_carry = 0;
+    const int nquads = (total + 3) >> 2;
+    int4* s4 = reinterpret_cast<int4*>(smem);
+    for (int k = threadIdx.x; k < nquads; k += kThreads) s4[k] = make_int4(0, 0, 0, 0);
     __syncthreads();
     for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
         const int32_t s = __ldg(c0 + i), e = __ldg(c1 + i);
@@ -481,13 +486,16 @@ __global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const in
         if (down < len) atomicAdd(&d[down], -1);
     }
     __syncthreads();
-    // in-place inclusive scan of smem[0, total)
+    // pass 1: every warp scans its own contiguous part in place (cumsum, src/bamsignals.cpp:464-470)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int32_t* base = smem;
-    for (int c0i = 0; c0i < total; c0i += kThreads * 4) {
-        const int idx = c0i + threadIdx.x * 4;
+    constexpr int kWarps = kThreads / 32;
+    const int qpw = ((nquads + kWarps - 1) / kWarps + 31) & ~31;          // quads per warp, whole warp steps
+    const int q_lo = wid * qpw, q_hi = min(nquads, q_lo + qpw);
+    int carry = 0;
+    for (int q0 = q_lo; q0 < q_hi; q0 += 32) {                            // warp-uniform
+        const int q = q0 + lane;
         int4 v = make_int4(0, 0, 0, 0);
-        if (idx < total) v = *reinterpret_cast<const int4*>(base + idx);   // tail ints beyond len are zero
+        if (q < q_hi) v = s4[q];
         v.y += v.x; v.z += v.y; v.w += v.z;
         int incl = v.w;
 #pragma unroll
@@ -495,20 +503,30 @@ __global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const in
             const int up = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += up;
         }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        int prefix = s_carry + incl - v.w;
-        for (int k = 0; k < wid; ++k) prefix += s_warp[k];
-        const int through = prefix + v.w;                    // inclusive sum through this thread's four ints
-        if (idx < total) {
-            v.x += prefix; v.y += prefix; v.z += prefix; v.w += prefix;
-            *reinterpret_cast<int4*>(base + idx) = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == kThreads - 1) s_carry = through;
-        __syncthreads();
+        const int prefix = carry + incl - v.w;
+        if (q < q_hi) { v.x += prefix; v.y += prefix; v.z += prefix; v.w += prefix; s4[q] = v; }
+        carry += __shfl_sync(FULL, incl, 31);
     }
-    copy_out(out + off, d, len);
+    if (lane == 0) s_warp[wid] = carry;
+    __syncthreads();
+    // pass 2: add the totals of the warps in front and stream the warp's own part out (128-bit streaming stores; the
+    // first and the last quad of the tile may be partial)
+    int before = 0;
+    for (int k = 0; k < wid; ++k) before += s_warp[k];
+    int32_t* dst = out + off - ph;                           // dst[j] <-> smem[j]; 16-byte aligned by construction
+    for (int q = q_lo + lane; q < q_hi; q += 32) {
+        int4 v = s4[q];
+        v.x += before; v.y += before; v.z += before; v.w += before;
+        const int j = 4 * q;
+        if (j >= ph && j + 4 <= total) {
+            __stcs(reinterpret_cast<int4*>(dst + j), v);
+        } else {
+            if (j >= ph && j < total) __stcs(dst + j, v.x);
+            if (j + 1 >= ph && j + 1 < total) __stcs(dst + j + 1, v.y);
+            if (j + 2 >= ph && j + 2 < total) __stcs(dst + j + 2, v.z);
+            if (j + 3 >= ph && j + 3 < total) __stcs(dst + j + 3, v.w);
+        }
+    }
 }
 
 void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
@@ -523,18 +541,18 @@ void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
 
 void launch_decode(const DecodeBatch& one, ReadTable t, bool coverage, const FilterParams& p, DeviceScalars* sc, cudaStream_t s) {
     if (one.n <= 0) return;
-    const int grid = (one.n + kThreads - 1) / kThreads;
+    const int grid = (one.n + kDecThreads - 1) / kDecThreads;
     DecodeBatch b = one;
     b.chunk0 = 0;
-    if (coverage) k_decode<true><<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
-    else k_decode<false><<<unsigned(grid), kThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
+    if (coverage) k_decode<true><<<unsigned(grid), kDecThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
+    else k_decode<false><<<unsigned(grid), kDecThreads, kSpanCap + 32, s>>>(b, nullptr, 1, t, p, sc);
 }
 
 void launch_decode_table(const DecodeBatch* d_table, int n_batches, int total_chunks, ReadTable t, bool coverage,
                          const FilterParams& p, DeviceScalars* sc, cudaStream_t s) {
     if (n_batches <= 0 || total_chunks <= 0) return;
-    if (coverage) k_decode<true><<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
-    else k_decode<false><<<unsigned(total_chunks), kThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
+    if (coverage) k_decode<true><<<unsigned(total_chunks), kDecThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
+    else k_decode<false><<<unsigned(total_chunks), kDecThreads, kSpanCap + 32, s>>>(DecodeBatch{}, d_table, n_batches, t, p, sc);
 }
 
 void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s) {

@@ -64,7 +64,10 @@ struct DecodeBatch {
     int32_t n;              // records
     int32_t chunk0;         // first 256-record chunk of this batch in a multi-batch launch
 };
-constexpr int kDecodeChunk = 256;
+#ifndef BSG_DECODE_THREADS
+#define BSG_DECODE_THREADS 128
+#endif
+constexpr int kDecodeChunk = BSG_DECODE_THREADS;     // records per K1 CTA (one thread per record)
 
 // K1 (decode + filter, fused): raw record bytes -> read table rows [row0, row0 + n).  Replaces bam_read1's field
 // extraction, bam_endpos (src/bamsignals.cpp:16-18) and setRead (:326-346 pileup, :392-415 coverage).

@@ -75,6 +75,13 @@ struct SmemAccess {
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + byte_off) : "memory");
         return r;
     }
+    __device__ __forceinline__ uint32_t sub_if(bool take, uint32_t byte_off, uint32_t otherwise) const {     // predicated
+        constexpr uint32_t off = offsetof(inflate_core::Tables, lit_sub);
+        uint32_t r = otherwise;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u16 %0, [%1]; }"
+                     : "+r"(r) : "r"(lit_a + off + byte_off), "r"(uint32_t(take)) : "memory");
+        return r;
+    }
     __device__ __forceinline__ uint32_t count(uint32_t len) const {
         constexpr uint32_t off = offsetof(inflate_core::Tables, dist_count);
         uint32_t r;
@@ -177,8 +184,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
         bool fin = true;
         InflateBlock blk{0u, 0u, 0u, 0u};
         BitReader br;
-        br.base = reinterpret_cast<const uint32_t*>(comp);  // cudaMalloc'ed: aligned
-        br.wi = br.w0 = br.w1 = br.w2 = br.bo = 0;
+        br.base = reinterpret_cast<const uint64_t*>(comp);  // cudaMalloc'ed: aligned
+        br.wi = br.a0 = br.a1 = br.b0 = br.b1 = br.p0 = br.p1 = br.bo = 0;
         SmemAccess acc{0u, 0u, 0u};
         if (is_dec) {
             fin = b0 + s >= n_blocks;
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         const int h = read_block_header(br, S[s].T, reinterpret_cast<uint8_t*>(q), &last);
                         if (h == 2) state = 2;
                         else if (h == 1) {           // stored block: LEN, NLEN, then LEN bytes that a copy warp moves
-                            br.consume((32u - br.bo) & 7u);
+                            br.consume((0u - br.bo) & 7u);
                             const uint32_t v = br.peek();
                             br.consume(32);
                             const uint32_t len = v & 0xffffu, nlen = v >> 16;

@@ -63,54 +63,57 @@ BSG_HD uint32_t rev_bits(uint32_t code, uint32_t len) {
 #endif
 }
 
-// Bit reader over aligned 32-bit words with two words of look-ahead: peek() is one funnel shift, consume() is an
-// add plus a predicated word rotation whose load was issued a word earlier.  Positions are 32-bit word indices into
-// one 4-byte aligned buffer (the batch's compressed bytes), so the state is five 32-bit registers.
+// Bit reader over aligned 64-bit units: A = (a1:a0) and B = (b1:b0) are the 128-bit window, bo < 64 is the bit offset
+// into it (so at least 64 valid bits: a token needs at most 52), P = (p1:p0) is the unit in flight.  A token consumes at
+// most 48 bits, so there is at most ONE refill per token, written without a branch (selects + a predicated load), and
+// the load issued at one refill is first touched at the NEXT refill of that lane (B = P), 64 consumed bits later.
+// Why it is built this way: 32 lanes decode 32 streams in lock step, so some lane refills in nearly every step.  With a
+// window of 32-bit words a token could need two refills; the second one was a (rare) branch, and at its join the compiler
+// copied the register of the load in flight - every step then waited for a global load (ncu: a third of the decode
+// warps' time on that one MOV).
 struct BitReader {
-    const uint32_t* base;  // the buffer (uniform for all blocks of a launch)
-    uint32_t wi;           // index of the next word to load
-    uint32_t w0, w1, w2, bo;
-    // One lane per stream reads its compressed bytes word by word.  L1 is filled by 32-byte SECTOR: the sector a word
-    // lives in serves eight refills of that lane if it stays in L1 (the copy warps' loads bypass L1 for that reason), and
-    // the sector two ahead is requested whenever the reader enters a sector, ~35 tokens before its first word is needed.
-    // (ncu before this: a third of the decode warps' time was the refill waiting for its word from L2 / DRAM - a shifting
-    // register window cannot look further ahead than one refill, the move of the pending word waits for it.)
-    BSG_HD void next_sector() const {
-#if defined(__CUDA_ARCH__)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 16u));
-#endif
-    }
-    BSG_HD void init(const uint32_t* buf, uint32_t byte_off) {
-        base = buf;
-        wi = byte_off >> 2;
-        bo = (byte_off & 3u) * 8u;
-        w0 = base[wi]; w1 = base[wi + 1]; w2 = base[wi + 2];
+    const uint64_t* base;  // the buffer (uniform for all blocks of a launch; 8-byte aligned)
+    uint32_t wi;           // index of the next 64-bit unit to load
+    uint32_t a0, a1, b0, b1, p0, p1, bo;
+    BSG_HD static void ld2(const uint64_t* p, uint32_t& lo, uint32_t& hi) { const uint64_t v = *p; lo = uint32_t(v); hi = uint32_t(v >> 32); }
+    BSG_HD void init(const void* buf, uint32_t byte_off) {
+        base = static_cast<const uint64_t*>(buf);
+        wi = byte_off >> 3;
+        bo = (byte_off & 7u) * 8u;
+        ld2(base + wi, a0, a1); ld2(base + wi + 1, b0, b1); ld2(base + wi + 2, p0, p1);
         wi += 3;
 #if defined(__CUDA_ARCH__)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + 8u));
+        // the batch has just arrived over PCIe: ask L2 for the lines ahead (one more whenever the reader enters a line)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + 16u));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + 32u));
 #endif
-        next_sector();
     }
-    BSG_HD uint32_t peek() const { return funnel_r(w0, w1, bo); }           // next 32 bits
-    BSG_HD uint32_t peek_hi() const { return funnel_r(w1, w2, bo); }        // the 32 bits after those
-    BSG_HD void refill() {
-        bo -= 32; w0 = w1; w1 = w2; w2 = base[wi];
-        if ((wi & 7u) == 0u) next_sector();
-        ++wi;
+    BSG_HD uint32_t peek() const {                                            // next 32 bits
+        const bool h = bo >= 32u;
+        return funnel_r(h ? a1 : a0, h ? b0 : a1, bo);
     }
-    BSG_HD void consume_short(uint32_t n) {                                   // n <= 32
-        bo += n;
-        if (bo >= 32) refill();
+    BSG_HD uint32_t peek_hi() const {                                         // the 32 bits after those
+        const bool h = bo >= 32u;
+        return funnel_r(h ? b0 : a1, h ? b1 : b0, bo);
     }
     BSG_HD void consume(uint32_t n) {                                         // n <= 64
         bo += n;
-        if (bo >= 32) {
-            refill();
-            if (bo >= 32) refill();
-        }
+        const bool rf = bo >= 64u;
+        bo = rf ? bo - 64u : bo;
+        a0 = rf ? b0 : a0; a1 = rf ? b1 : a1;
+        b0 = rf ? p0 : b0; b1 = rf ? p1 : b1;
+#if defined(__CUDA_ARCH__)
+        asm volatile("{ .reg .pred p, q; .reg .b32 t; setp.ne.u32 p, %3, 0; @p ld.global.v2.u32 {%0, %1}, [%2];\n\t"
+                     "and.b32 t, %4, 15; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L2 [%2 + 256]; }"
+                     : "+r"(p0), "+r"(p1) : "l"(base + wi), "r"(uint32_t(rf)), "r"(wi) : "memory");
+#else
+        if (rf) ld2(base + wi, p0, p1);
+#endif
+        wi += rf ? 1u : 0u;
     }
-    BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 32u + bo; }  // bits from the start of the buffer
-    BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 4u + (bo >> 3); }   // only valid when bo is a multiple of 8
+    BSG_HD void consume_short(uint32_t n) { consume(n); }
+    BSG_HD uint64_t bit_pos() const { return uint64_t(wi - 3u) * 64u + bo; }  // bits from the start of the buffer
+    BSG_HD uint32_t byte_pos() const { return (wi - 3u) * 8u + (bo >> 3); }   // only valid when bo is a multiple of 8
 };
 
 struct Tables {
@@ -264,32 +267,41 @@ BSG_HD bool build_lit_table(const uint8_t* lens, Tables& T) {
             if (pre < pmin) pmin = pre;
         }
     }
-    if (pmin == (1 << kRoot)) return true;                            // no long codes
+    // (no early return for "no long codes" and none inside the loops below: 32 lanes build 32 tables in lock step, and a
+    // loop with a second exit has no reconvergence point behind it - the lanes ran everything after it, pass 3 included,
+    // one lane after the other: ncu showed 1.5 active lanes and half of all instructions of the block-header phase there)
     // pass 2: long codes own the top of the code space: give every prefix from pmin up its second-level table
     int off = 0;
+    bool fits = true;
     for (int pre = pmin; pre < (1 << kRoot); ++pre) {
         uint16_t& slot = T.lit[rev_bits(uint32_t(pre), kRoot)];
         const uint32_t e = slot;
-        if ((e & (kNonLit | (7u << kClsShift))) != kLitUnset || !(e & 15u)) continue;    // a short code, or nothing at all
-        const int bits = int(e & 15u), size = 1 << bits;
-        if (off + size > kLitSub) return false;
-        slot = uint16_t(kLitUnset | uint32_t(bits) | (uint32_t(off >> 1) << 8));
-        for (int j = 0; j < size; ++j) T.lit_sub[off + j] = uint16_t(kLitUnset);
-        off += size;
+        if ((e & (kNonLit | (7u << kClsShift))) == kLitUnset && (e & 15u)) {              // neither a short code nor nothing at all
+            const int bits = int(e & 15u), size = 1 << bits;
+            if (off + size > kLitSub) fits = false;
+            else {
+                slot = uint16_t(kLitUnset | uint32_t(bits) | (uint32_t(off >> 1) << 8));
+                for (int j = 0; j < size; ++j) T.lit_sub[off + j] = uint16_t(kLitUnset);
+                off += size;
+            }
+        }
     }
-    // pass 3: the long codes themselves
+    // pass 3: the long codes themselves (a prefix whose table did not fit keeps [15:8] = 0 and [3:0] = its bits: the
+    // writes below then stay inside lit_sub, and the block is refused)
     for (int l = 0; l < 16; ++l) next[l] = first_code[l];
     for (int s = 0; s < n; ++s) {
         const int l = lens[s] & 15;
-        if (!l) continue;
-        const uint32_t code = uint32_t(next[l]++);
-        if (l <= kRoot) continue;
-        const int rest = l - kRoot;
-        const uint32_t link = T.lit[rev_bits(code >> rest, kRoot)];
-        const int bits = int(link & 15u), base = int(link >> 8) * 2;
-        const uint16_t e = uint16_t(lit_entry(s, l));
-        for (int k = int(rev_bits(code & ((1u << rest) - 1u), uint32_t(rest))); k < (1 << bits); k += (1 << rest)) T.lit_sub[base + k] = e;
+        const uint32_t code = uint32_t(next[l]++);                     // next[0] is never used for a code
+        if (l > kRoot) {
+            const int rest = l - kRoot;
+            const uint32_t link = T.lit[rev_bits(code >> rest, kRoot)];
+            const int bits = int(link & 15u), base = int(link >> 8) * 2;
+            const uint16_t e = uint16_t(lit_entry(s, l));
+            if (fits)
+                for (int k = int(rev_bits(code & ((1u << rest) - 1u), uint32_t(rest))); k < (1 << bits); k += (1 << rest)) T.lit_sub[base + k] = e;
+        }
     }
+    if (!fits) return false;
     return true;
 }
 
@@ -378,6 +390,37 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
     uint32_t op = *op_dec;
     int err = 0;
     *eob = 0;
+#if defined(__CUDA_ARCH__)
+    do {
+        const uint32_t v = br.peek();
+        uint32_t e = acc.lit((v << 1) & kLitMask2);
+        {   // a code longer than the primary table: second-level lookup, predicated (some lane needs it in most steps)
+            const bool lng = (e & kClassMask) == kLitUnset;
+            const uint32_t sb = e & 15u;
+            err |= int(lng & (sb == 0u));                                      // no such code
+            e = acc.sub_if(lng, (e >> 8) * 4u + (((v >> kLitBits) & ~(~0u << sb)) << 1), e);
+        }
+        const bool is_lit = !(e & kNonLit);
+        const uint32_t cls = (e >> kClsShift) & 7u;
+        if (!is_lit & (cls >= kClsOther)) {           // end of block, or garbage
+            if (cls == kClsEob) { br.consume_short(e & 15u); *eob = 1; } else err = 1;
+            break;
+        }
+        const uint32_t len = e & 15u, eb = is_lit ? 0u : cls, used = len + eb;      // eb = number of extra bits
+        const uint32_t mlen = (e >> 8) + 3u + ((v >> len) & ~(~0u << eb));
+        const uint32_t v2 = funnel_r(v, br.peek_hi(), used);      // used <= 20
+        uint32_t d = acc.dist((v2 << 1) & kDistMask2);
+        if (!is_lit & !(d & 15u)) d = slow_entry(v2, acc);
+        const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
+        uint32_t mdist = (((d >> 8) & 3u) << deb) + 1u + ((v2 >> dl) & ~(~0u << deb));
+        br.consume(is_lit ? len : used + dl + deb);                // <= 48
+        const bool badm = !is_lit & (((d & kDistBad) != 0u) | (mdist > op));
+        err |= int(badm);
+        mdist = badm ? 1u : mdist;
+        acc.put(qo, is_lit ? (e >> 8) : (kTokMatch | ((mdist - 1u) << 16) | mlen));
+        qo += 4; op += is_lit ? 1u : mlen;
+    } while (qo < uint32_t(kQueue) * 4u);
+#else
     do {
         const uint32_t v = br.peek();
         uint32_t e = acc.lit((v << 1) & kLitMask2);
@@ -404,6 +447,7 @@ BSG_HD int fill_queue(BR& br, const A& acc, uint32_t* op_dec, int* eob, int* bad
         acc.put(qo, is_lit ? (e >> 8) : (kTokMatch | ((mdist - 1u) << 16) | mlen));
         qo += 4; op += is_lit ? 1u : mlen;
     } while (qo < uint32_t(kQueue) * 4u);
+#endif
     *op_dec = op;
     *bad |= err;
     return int(qo >> 2);

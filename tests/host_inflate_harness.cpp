@@ -28,7 +28,7 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
             const int h = read_block_header(br, T, reinterpret_cast<uint8_t*>(q), &last);
             if (h == 2) return 2;
             if (h == 1) {
-                br.consume((32 - br.bo) & 7);
+                br.consume((0u - br.bo) & 7u);
                 const uint32_t v = br.peek();
                 br.consume(32);
                 const uint32_t len = v & 0xffffu, nlen = v >> 16;

@@ -56,7 +56,7 @@ def main():
                                        inflate=t["ms_inflate_gpu"], h2d=t["ms_h2d"], kernels=t["ms_kernels"], batches=t["n_batches"]))
     out = {}
     for label, rows in res.items():
-        out[label] = {k: round(sorted(r[k] for r in rows)[len(rows) // 2], 2) for k in rows[0]}
+        out[label] = {k: round(sorted(r[k] for r in rows)[len(rows) // 2], 2) for k in rows[0]} if rows else {}
     print(json.dumps({"preset": a.preset, "gscale": a.gscale, "reads": info["records"], "median_ms": out}))
 
 

@@ -53,6 +53,7 @@ constexpr uint64_t kSmallJobBytes = 16u << 20;   // inflated bytes up to which t
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
 constexpr int kOutSlots = 3;                    // pinned result-staging ring
+constexpr int kUp = 4;                          // GPU-inflate path: upload ring (compressed bytes + descriptors); raw buffers: 2
 
 struct DevBuf {
     void* p = nullptr;
@@ -95,9 +96,10 @@ struct DeviceCtx {
     DevBuf tab[2], c0, c1, tiles_i32, tiles_i64, out, scalars;
     uint64_t tiles_gen = 0;                     // bumped whenever a Session uploads tiles: a staged Session's cached tiles are
                                                 // only valid while no other call has replaced them on this device
-    DevBuf g_comp[2], g_raw[2], g_offs[2], g_blocks[2], g_crc[2], g_walkers[2], g_counts[2], g_base[2], g_total;   // GPU inflate ring
-    PinBuf h_total, h_desc[2];
-    cudaEvent_t ev_pin[kSlots] = {}, ev_total[2] = {}, ev_gfree[2] = {}, ev_inflated[2] = {}, ev_crc[2] = {};
+    // GPU inflate: an upload ring of kUp slots (compressed bytes, descriptors, walk scratch) and two raw / offsets buffers
+    DevBuf g_comp[kUp], g_blocks[kUp], g_crc[kUp], g_walkers[kUp], g_counts[kUp], g_base[kUp], g_raw[2], g_offs[2], g_total;
+    PinBuf h_total, h_desc[kUp];
+    cudaEvent_t ev_pin[kSlots] = {}, ev_up[kUp] = {}, ev_total[kUp] = {}, ev_inflated[kUp] = {}, ev_crc[kUp] = {}, ev_gfree[2] = {};
     PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front;
     cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {}, ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
@@ -126,14 +128,17 @@ struct DeviceCtx {
         h_front.ensure(64);
         for (int i = 0; i < 2; ++i) {
             BSG_CUDA(cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming));
-            BSG_CUDA(cudaEventCreateWithFlags(&ev_total[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_gfree[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < kUp; ++i) {
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+            BSG_CUDA(cudaEventCreateWithFlags(&ev_total[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_inflated[i], cudaEventDisableTiming));
             BSG_CUDA(cudaEventCreateWithFlags(&ev_crc[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < kSlots; ++i) BSG_CUDA(cudaEventCreateWithFlags(&ev_pin[i], cudaEventDisableTiming));
-        h_total.ensure(64);
-        g_total.ensure(64);
+        h_total.ensure(64 + 4 * kUp);
+        g_total.ensure(64 + 4 * kUp);
         h_scalars.ensure(sizeof(DeviceScalars));
         init = true;
     }
@@ -159,13 +164,14 @@ struct DeviceCtx {
         for (int i = 0; i < kOutSlots; ++i) { h_out[i].release(); cudaEventDestroy(ev_d2h[i]); }
         h_tiles.release(); h_front.release();
         cudaEventDestroy(ev_front[0]); cudaEventDestroy(ev_front[1]);
-        for (int i = 0; i < 2; ++i) {
-            g_comp[i].release(); g_raw[i].release(); g_offs[i].release(); g_blocks[i].release(); g_crc[i].release(); g_walkers[i].release();
-            g_counts[i].release(); g_base[i].release(); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_gfree[i]);
-            cudaEventDestroy(ev_inflated[i]); cudaEventDestroy(ev_crc[i]);
+        for (int i = 0; i < 2; ++i) { g_raw[i].release(); g_offs[i].release(); cudaEventDestroy(ev_gfree[i]); }
+        for (int i = 0; i < kUp; ++i) {
+            g_comp[i].release(); g_blocks[i].release(); g_crc[i].release(); g_walkers[i].release();
+            g_counts[i].release(); g_base[i].release(); h_desc[i].release();
+            cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_inflated[i]); cudaEventDestroy(ev_crc[i]);
         }
         for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev_pin[i]);
-        g_total.release(); h_total.release(); h_desc[0].release(); h_desc[1].release();
+        g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
         cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
@@ -1053,9 +1059,14 @@ private:
     }
 
     // GPU-inflate pipeline: host ships compressed bytes; inflate, record walk and decode run on the device.
-    // Batch b: [host: descriptors + memcpy file -> pinned chunks -> H2D] -> inflate -> walk (count/scan/write) ->
-    // total read-back; K1 for batch b is launched one iteration later so that the host work of batch b+1 overlaps the
-    // device work of batch b.
+    //   upload(b):  descriptors + H2D of the compressed bytes into upload slot b % kUp              (copy stream)
+    //   compute(b): inflate -> CRC (side stream) -> walk (count / scan / write) -> record count back (compute stream)
+    //   finish(b):  K1 decode on the high-priority stream, frontier read-back, count + ship the tiles it finalises
+    // The inflate kernel is persistent and takes every SM (227 KB of shared memory per CTA): K1 of batch b, launched when
+    // the host has seen the walk of b end, runs only when inflate(b + 1) has drained, and finish(b) blocks the host
+    // until then.  Everything that must not wait for that is therefore queued BEFORE finish(b): compute(b + 1) and
+    // upload(b + 2).  (Round 1 queued upload(b + 1) after finish(b - 1): each H2D started when an inflate ended, copy
+    // engine and SMs took turns - 88 ms for C2 whose kernels need 51 ms and whose H2D needs 37.)
     void run_pipeline_gpu(uint64_t max_batch, size_t max_offs) {
         DeviceCtx& c = *ctx_;
         const size_t nb = batches_.size();
@@ -1063,50 +1074,16 @@ private:
         n_rows_ = 0;
         const std::vector<uint64_t>& ent = bam_.entry_points();
         uint64_t raw_base = 0; int64_t offs_base = 0;
-        struct Pending { bool valid = false; int slot = 0; uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0; };
-        Pending pend;
+        struct Up {             // what compute() and finish() need to know about an uploaded batch
+            int n_blocks = 0, n_walkers = 0; uint32_t end_pos = 0;
+            uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0;
+        };
+        std::vector<Up> ups(nb);
         // the high-priority stream starts behind everything already queued on the compute stream (scalars reset, tiles)
         hi_prio_ = !keep_raw_;
         BSG_CUDA(cudaEventRecord(c.ev_order, c.s_comp));
         BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_order, 0));
         std::vector<Span> inflate_spans, walk_spans, h2d_spans;
-        auto finish = [&](Pending& p) {
-            if (!p.valid) return;
-            BSG_CUDA(cudaEventSynchronize(c.ev_total[p.slot]));
-            const int64_t n = int64_t(c.h_total.as<uint32_t>()[p.slot]);
-            if (n_rows_ + n > rows_cap_) fail(BSG_EFORMAT, "record count exceeds the planned table capacity");
-            if (keep_raw_) {
-                resident_.push_back(ResidentBatch{p.raw_base, p.offs_base, n});
-            } else {
-                // decode on the high-priority stream as soon as the walk of this batch is done (ev_total): it overtakes
-                // the inflate of the next batch, which is already queued on the compute stream
-                BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_total[p.slot], 0));
-                Span sp{c.timing_event(), c.timing_event()};
-                BSG_CUDA(cudaEventRecord(sp.a, c.s_hi));
-                if (!cnt_.active) fail(BSG_EARG, "internal error: streaming decode without a counting call");
-                launch_decode(DecodeBatch{p.d_raw, p.d_offs, n_rows_, int32_t(n), 0}, table(), cnt_.mode == MODE_COVERAGE, cnt_.fp,
-                              c.scalars.as<DeviceScalars>(), c.s_hi);
-                BSG_CUDA(cudaEventRecord(sp.b, c.s_hi));
-                kt_.decode.push_back(sp); kt_.launches += n > 0;
-                if (n > 0 && cnt_.active) {
-                    // (tid, pos) of the last decoded record = how far the sorted read stream has come: count + ship
-                    // every tile it finalises while the next batch inflates
-                    // (Polling for the frontier between upload chunks instead of blocking here was measured: no gain.)
-                    ReadTable t = table();
-                    int32_t* f = c.h_front.as<int32_t>();
-                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
-                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
-                    BSG_CUDA(cudaEventRecord(c.ev_front[0], c.s_hi));
-                    BSG_CUDA(cudaEventSynchronize(c.ev_front[0]));
-                    advance(n_rows_ + n, uint32_t(f[0]), f[1]);
-                }
-            }
-            cudaStream_t fs = keep_raw_ ? c.s_comp : c.s_hi;
-            if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(fs, c.ev_crc[p.slot], 0));
-            BSG_CUDA(cudaEventRecord(c.ev_gfree[p.slot], fs));
-            n_rows_ += n;
-            p.valid = false;
-        };
         double t_desc = 0, t_copy = 0, t_wait = 0, t_finish = 0;
         std::vector<InflateBlock> blocks;
         std::vector<uint32_t> crcs;
@@ -1114,9 +1091,11 @@ private:
         struct CopyPiece { uint64_t file_off, dst_off, len; };
         std::vector<CopyPiece> pieces;
         int pin_slot = 0;
-        for (size_t bi = 0; bi < nb; ++bi) {
+
+        auto upload = [&](size_t bi) {
             Batch* b = batches_[bi].get();
-            const int slot = int(bi & 1);
+            const int slot = int(bi % kUp), rslot = int(bi & 1);
+            Up& up = ups[bi];
             // ---- descriptors -----------------------------------------------------------------------------------------
             double tt = now_ms();
             nvtxRangePushA("bsg:batch descriptors");
@@ -1165,10 +1144,8 @@ private:
             nvtxRangePop();
             t_desc += now_ms() - tt; tt = now_ms();
             // ---- buffers ------------------------------------------------------------------------------------------------
-            // The upload overwrites only the compressed bytes and the descriptor arrays of this slot; their readers are
-            // the inflate, walk and CRC kernels of the batch before last.  The slot's RAW buffer is still being read by
-            // that batch's decode kernel, but it is written next by this batch's inflate: a device-side dependency
-            // (stream wait below), not a reason to hold the upload back.
+            // The upload overwrites the compressed bytes, descriptor arrays and walk scratch of its slot; their readers
+            // were the inflate, walk and CRC kernels of batch bi - kUp, finished long ago (no wait in practice).
             BSG_CUDA(cudaEventSynchronize(c.ev_total[slot]));
             BSG_CUDA(cudaEventSynchronize(c.ev_crc[slot]));
             t_wait += now_ms() - tt; tt = now_ms();
@@ -1179,16 +1156,19 @@ private:
             c.g_walkers[slot].ensure(walkers.size() * sizeof(uint2) + 64);
             c.g_counts[slot].ensure(walkers.size() * 4 + 64);
             c.g_base[slot].ensure(walkers.size() * 4 + 64);
-            uint8_t* d_raw; uint32_t* d_offs;
             if (keep_raw_) {
-                d_raw = raw_all_.as<uint8_t>() + raw_base;
-                d_offs = offs_all_.as<uint32_t>() + offs_base;
+                up.d_raw = raw_all_.as<uint8_t>() + raw_base;
+                up.d_offs = offs_all_.as<uint32_t>() + offs_base;
             } else {
-                c.g_raw[slot].ensure(max_batch + 64);
-                c.g_offs[slot].ensure((max_offs + 8) * sizeof(uint32_t));
-                d_raw = c.g_raw[slot].as<uint8_t>();
-                d_offs = c.g_offs[slot].as<uint32_t>();
+                // the raw buffer of the slot may still be read by the decode kernel of batch bi - 2; this batch's inflate
+                // writes it next: a device-side dependency (ev_gfree in compute()), not a reason to hold the upload back
+                c.g_raw[rslot].ensure(max_batch + 64);
+                c.g_offs[rslot].ensure((max_offs + 8) * sizeof(uint32_t));
+                up.d_raw = c.g_raw[rslot].as<uint8_t>();
+                up.d_offs = c.g_offs[rslot].as<uint32_t>();
             }
+            up.raw_base = raw_base; up.offs_base = offs_base;
+            up.n_blocks = int(blocks.size()); up.n_walkers = int(walkers.size()); up.end_pos = end_pos;
             // ---- compressed bytes -> device ------------------------------------------------------------------------------------
             Span sph{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sph.a, c.s_copy));
@@ -1258,61 +1238,108 @@ private:
                 if (nb_c && opts_.verify_crc) BSG_CUDA(cudaMemcpyAsync(c.g_crc[slot].p, hd + o_c, nb_c, cudaMemcpyHostToDevice, c.s_copy));
                 if (nb_w) BSG_CUDA(cudaMemcpyAsync(c.g_walkers[slot].p, hd + o_w, nb_w, cudaMemcpyHostToDevice, c.s_copy));
             }
-            BSG_CUDA(cudaEventRecord(c.ev_h2d[slot], c.s_copy));
+            BSG_CUDA(cudaEventRecord(c.ev_up[slot], c.s_copy));
             BSG_CUDA(cudaEventRecord(sph.b, c.s_copy));
             h2d_spans.push_back(sph);
             nvtxRangePop();
-            t_copy += now_ms() - tt; tt = now_ms();
-            nvtxRangePushA("bsg:launch inflate + crc + walk");
-            // ---- device: inflate -> walk -> total ------------------------------------------------------------------------------
-            BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[slot], 0));
-            BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_gfree[slot], 0));       // decode (+ CRC) of the slot's previous batch
-            Span sp{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
-            launch_inflate(c.g_blocks[slot].as<InflateBlock>(), int(blocks.size()), c.g_comp[slot].as<uint8_t>(), d_raw,
-                           c.scalars.as<DeviceScalars>(), c.s_comp);
-            if (opts_.verify_crc) {
-                // integrity check on a side stream: it only reads the inflated bytes, so it overlaps walk + decode of this
-                // batch and the inflate of the next one; the slot is not recycled before it has finished (finish()).
-                BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
-                BSG_CUDA(cudaStreamWaitEvent(c.s_aux, c.ev_inflated[slot], 0));
-                launch_crc32(c.g_blocks[slot].as<InflateBlock>(), c.g_crc[slot].as<uint32_t>(), int(blocks.size()), d_raw,
-                             c.scalars.as<DeviceScalars>(), c.s_aux);
-                BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
-                kt_.launches += blocks.empty() ? 0 : 1;
-            }
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
-            inflate_spans.push_back(sp);
-            // The record walk stays on the compute stream, between this batch's inflate and the next one's.  (Measured:
-            // on the high-priority stream its three small kernels cannot start while the next inflate holds every SM at
-            // full register occupancy - C2 143 -> 181 ms.)
-            cudaStream_t ws = c.s_comp;
-            Span spw{c.timing_event(), c.timing_event()};
-            BSG_CUDA(cudaEventRecord(spw.a, ws));
-            launch_walk(d_raw, c.g_walkers[slot].as<uint2>(), int(walkers.size()), c.g_counts[slot].as<uint32_t>(),
-                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, d_offs, end_pos,
-                        c.scalars.as<DeviceScalars>(), ws);
-            BSG_CUDA(cudaEventRecord(spw.b, ws));
-            walk_spans.push_back(spw);
-            kt_.launches += (blocks.empty() ? 0 : 1) + (walkers.empty() ? 1 : 3);
-            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ws));
-            BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));
-            nvtxRangePop();
-            // ---- previous batch: decode ------------------------------------------------------------------------------------------
-            tt = now_ms();
-            nvtxRangePushA("bsg:decode previous batch + stream out");
-            finish(pend);
-            nvtxRangePop();
-            t_finish += now_ms() - tt;
-            pend.valid = true; pend.slot = slot; pend.d_raw = d_raw; pend.d_offs = d_offs; pend.raw_base = raw_base; pend.offs_base = offs_base;
+            t_copy += now_ms() - tt;
             if (keep_raw_) {
                 raw_base += (b->bytes + 64 + 255) & ~255ull;
                 offs_base += int64_t((b->bytes) / kMinRecord) + 2;
             }
+        };
+
+        auto compute = [&](size_t bi) {
+            const int slot = int(bi % kUp), rslot = int(bi & 1);
+            const Up& up = ups[bi];
+            nvtxRangePushA("bsg:launch inflate + crc + walk");
+            BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_up[slot], 0));
+            if (!keep_raw_) BSG_CUDA(cudaStreamWaitEvent(c.s_comp, c.ev_gfree[rslot], 0));      // decode (+ CRC) of batch bi - 2
+            Span sp{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
+            launch_inflate(c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, c.g_comp[slot].as<uint8_t>(), up.d_raw,
+                           c.scalars.as<DeviceScalars>(), c.s_comp);
+            if (opts_.verify_crc) {
+                // integrity check on a side stream: it only reads the inflated bytes, so it overlaps walk + decode of this
+                // batch; the raw buffer is not recycled before it has finished (finish()).
+                BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
+                BSG_CUDA(cudaStreamWaitEvent(c.s_aux, c.ev_inflated[slot], 0));
+                launch_crc32(c.g_blocks[slot].as<InflateBlock>(), c.g_crc[slot].as<uint32_t>(), up.n_blocks, up.d_raw,
+                             c.scalars.as<DeviceScalars>(), c.s_aux);
+                BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
+                kt_.launches += up.n_blocks ? 1 : 0;
+            }
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            inflate_spans.push_back(sp);
+            // The record walk stays on the compute stream, between this batch's inflate and the next one's.  (Measured:
+            // on the high-priority stream its three small kernels cannot start while the next inflate holds every SM -
+            // C2 143 -> 181 ms.)
+            cudaStream_t ws = c.s_comp;
+            Span spw{c.timing_event(), c.timing_event()};
+            BSG_CUDA(cudaEventRecord(spw.a, ws));
+            launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, c.g_counts[slot].as<uint32_t>(),
+                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, up.d_offs, up.end_pos,
+                        c.scalars.as<DeviceScalars>(), ws);
+            BSG_CUDA(cudaEventRecord(spw.b, ws));
+            walk_spans.push_back(spw);
+            kt_.launches += (up.n_blocks ? 1 : 0) + (up.n_walkers ? 3 : 1);
+            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ws));
+            BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));
+            nvtxRangePop();
+        };
+
+        auto finish = [&](size_t bi) {
+            const int slot = int(bi % kUp), rslot = int(bi & 1);
+            const Up& up = ups[bi];
+            nvtxRangePushA("bsg:decode batch + stream out");
+            BSG_CUDA(cudaEventSynchronize(c.ev_total[slot]));
+            const int64_t n = int64_t(c.h_total.as<uint32_t>()[slot]);
+            if (n_rows_ + n > rows_cap_) fail(BSG_EFORMAT, "record count exceeds the planned table capacity");
+            if (keep_raw_) {
+                resident_.push_back(ResidentBatch{up.raw_base, up.offs_base, n});
+            } else {
+                // decode on the high-priority stream as soon as the walk of this batch is done (ev_total): it goes ahead of
+                // whatever of the next batches has not started yet
+                BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_total[slot], 0));
+                Span sp{c.timing_event(), c.timing_event()};
+                BSG_CUDA(cudaEventRecord(sp.a, c.s_hi));
+                if (!cnt_.active) fail(BSG_EARG, "internal error: streaming decode without a counting call");
+                launch_decode(DecodeBatch{up.d_raw, up.d_offs, n_rows_, int32_t(n), 0}, table(), cnt_.mode == MODE_COVERAGE, cnt_.fp,
+                              c.scalars.as<DeviceScalars>(), c.s_hi);
+                BSG_CUDA(cudaEventRecord(sp.b, c.s_hi));
+                kt_.decode.push_back(sp); kt_.launches += n > 0;
+                if (n > 0 && cnt_.active) {
+                    // (tid, pos) of the last decoded record = how far the sorted read stream has come: count + ship
+                    // every tile it finalises while the next batches inflate
+                    // (Polling for the frontier between upload chunks instead of blocking here was measured: no gain.)
+                    ReadTable t = table();
+                    int32_t* f = c.h_front.as<int32_t>();
+                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
+                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
+                    BSG_CUDA(cudaEventRecord(c.ev_front[0], c.s_hi));
+                    BSG_CUDA(cudaEventSynchronize(c.ev_front[0]));
+                    advance(n_rows_ + n, uint32_t(f[0]), f[1]);
+                }
+                if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_crc[slot], 0));
+                BSG_CUDA(cudaEventRecord(c.ev_gfree[rslot], c.s_hi));
+            }
+            n_rows_ += n;
+            nvtxRangePop();
+        };
+
+        if (nb > 0) upload(0);
+        if (nb > 1) upload(1);
+        if (nb > 0) compute(0);
+        for (size_t bi = 0; bi < nb; ++bi) {
+            if (bi + 1 < nb) compute(bi + 1);
+            if (bi + 2 < nb) upload(bi + 2);
+            const double tt = now_ms();
+            finish(bi);
+            t_finish += now_ms() - tt;
         }
-        finish(pend);
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_hi));
+        if (opts_.verify_crc) BSG_CUDA(cudaStreamSynchronize(c.s_aux));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
         tm_.ms_h2d = sum_ms(h2d_spans);         // on the copy stream: the time the copy engine (and, when staging, the pool) needed
         if (getenv("BSG_DEBUG"))

@@ -46,7 +46,7 @@ struct WsCtl {
     uint32_t pos[kWsStreams];                        // bytes materialised so far (owned by the stream's copy warp)
     uint32_t out_off[kWsStreams], out_len[kWsStreams];
     uint32_t produced[2][kWsDecWarps];               // did the decode warp hand over anything in round buf?
-    uint32_t bitmap[kWsCopyWarps][32];               // scratch of a copy warp while it builds a token-start bitmap
+    alignas(8) uint8_t stage[kWsCopyWarps][256];     // a copy warp's chunk of output being built (also its bitmap scratch)
 };
 constexpr size_t kWsSmem = sizeof(WsStream) * kWsStreams + sizeof(WsCtl);
 static_assert(sizeof(WsStream) % 8 == 0, "stream slots keep the tables aligned");
@@ -108,63 +108,163 @@ struct SmemAccess {
     }
 };
 
-// Copy side: FOUR queues (<= 32 tokens each, one token per lane) -> bytes, interleaved by one warp.
+// Copy side: a queue (<= 32 tokens, one token per lane) -> bytes, by one warp.
 //
-// Byte-parallel: in every step each lane produces ONE byte of 32 consecutive output bytes of a queue.  The lane finds the
-// token that owns its byte - a bitmap of token start positions (one 32-bit word per 32-byte step, 1024 bytes per
-// window) plus a prefix pop-count, moved between lanes with shuffles - and then where the byte comes from: the token's
-// literal, or `dist` bytes back.  A source in front of the step's 32 bytes is finished output (earlier steps, queues,
-// rounds) and is LOADED; a source inside them (distance < 32: rare) is chased through its own owner token instead; a match
-// that overlaps itself (dist < len) jumps in front of its own start with one modulo.  So the bytes of a step never wait
-// for each other.  A step does wait for the stores of the step before it (a record usually copies from the record in
-// front of it, 40-60 bytes back), and that round trip goes to L2 or - the 64 KiB windows of all resident streams are five
-// times the L2 - to DRAM: the warp therefore works on four queues at once, issuing the loads of all four before it
-// consumes any of them.
+// Byte-parallel: every lane produces ONE byte of 32 consecutive output bytes per step.  The lane finds the token that owns
+// its byte - a bitmap of token start positions (one 32-bit word per step, 1024 bytes per window) plus a prefix pop-count,
+// moved between lanes with shuffles - and then where the byte comes from: the token's literal, or `dist` bytes back (a
+// match that overlaps itself, dist < len, jumps in front of its own start with one modulo; a source inside the step's own
+// 32 bytes, distance < 32: rare, is chased through its owner token).
+// The output is built in CHUNKS of 256 bytes (eight steps) in a shared-memory stage owned by the warp:
+//   pass 1  resolves the eight bytes of every lane; a source in front of the chunk is finished output in global memory
+//           and its load is ISSUED (eight independent loads per lane in flight); a source inside the chunk is noted;
+//   pass 2  goes through the steps in order: bytes with a source inside the chunk read it from the stage (written by an
+//           earlier step: ~30 cycles instead of a trip to L2), every byte is put on the stage;
+//   pass 3  writes the chunk out with one 8-byte store per lane (the partial first / last word byte by byte).
+// So the warp waits for memory once per 256 bytes - for loads that were all issued before the first one is needed - and
+// what it waits for is usually a record several back, not the previous step's stores.
 // History (ncu, C2): token-per-lane copies in waves of matches that read each other's output: the copy warps sat on
-// dependent L2 round trips (22 % of all samples on one line) while the decode warps waited at the barrier (42 %), 10.0 ms
-// per wave of 9472 blocks; four bytes per lane chased through the whole window: ~10 rounds of shuffles per step, 10.7 ms;
-// chased through the 128 bytes of the step only: 5.5 rounds, 8.7 ms.
-constexpr int kQpw = 4;                              // queues per copy warp
+// dependent L2 round trips (22 % of all samples on one line) while the decode warps waited at the barrier, 10.0 ms per
+// wave of 9472 blocks; four bytes per lane chased through the whole window: ~10 rounds of shuffles per step, 10.7 ms;
+// chased through the 128 bytes of the step only: 5.5 rounds, 8.7 ms; one byte per lane, load -> store -> next step, four
+// queues interleaved per warp: 6.6 ms, then 5.5 ms with the faster decode side, the copy warps the bottleneck again
+// (half of the L2 reads miss: the 32 KiB windows of 9472 streams are 2.5x the L2, so every step waited for DRAM).
+constexpr int kQpw = 4;                              // queues (streams) per copy warp, one after the other
+constexpr int kChunk = 256;                          // bytes staged per chunk
+constexpr int kSteps = kChunk / 32;
 
-struct CopyQueue {
-    uint32_t t;                                      // this lane's token
-    int32_t s, e;                                    // it covers bytes [s, e) in u coordinates (byte u lives at al[u])
-    uint32_t bm, pre, firstk;                        // this lane's word of the start bitmap, starts before it, tokens before the window
-    uint8_t* al;                                     // the aligned word at or before the queue's first output byte
-    int32_t a0, end_u;                               // the queue's bytes are [a0, end_u)
-};
-
-// bitmap + prefix of window [wb, wb + 1024) of one queue; bm_s = 32 words of shared memory owned by the calling warp
-__device__ __forceinline__ void copy_window(CopyQueue& Q, int32_t wb, int lane, uint32_t* bm_s) {
-    const bool valid = Q.e > Q.s;
-    const int32_t wend = min(Q.end_u, wb + 1024);
-    // tokens that end at or before the window come first; then bit (start - wb) for every token in the window (a token
-    // that began before the window and reaches into it owns bit 0)
-    Q.firstk = uint32_t(__popc(__ballot_sync(FULL, valid && Q.e <= wb)));
-    bm_s[lane] = 0u;
-    __syncwarp();
-    if (valid && Q.e > wb && Q.s < wend) {
-        const uint32_t r = uint32_t(max(Q.s, wb) - wb);
-        atomicOr(&bm_s[r >> 5], 1u << (r & 31u));
-    }
-    __syncwarp();
-    Q.bm = bm_s[lane];
-    __syncwarp();
-    const uint32_t pc = uint32_t(__popc(Q.bm));
-    uint32_t inc = pc;
+// One queue -> bytes at first_byte; stage = kChunk bytes of shared memory owned by the warp (8-byte aligned).
+// Returns the number of bytes.
+__device__ __forceinline__ uint32_t materialise(const uint32_t* q, int nq, uint8_t* first_byte, int lane, uint8_t* stage) {
+    const bool valid = lane < nq;
+    const uint32_t t = valid ? q[lane] : 0u;
+    const uint32_t len = (t >> 31) ? (t & 0x1ffu) : (valid ? 1u : 0u);
+    uint32_t incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += up;
+        const uint32_t up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
     }
-    Q.pre = inc - pc;
-}
-
-// owner token of byte xx (window-relative lookup), generic: any lane may ask for any byte of the window
-__device__ __forceinline__ int copy_owner(const CopyQueue& Q, int32_t xx, int32_t wb) {
-    const uint32_t r = uint32_t(xx - wb);
-    const uint32_t m = __shfl_sync(FULL, Q.bm, int(r >> 5)), p = __shfl_sync(FULL, Q.pre, int(r >> 5));
-    return int((Q.firstk + p + uint32_t(__popc(m & ((2u << (r & 31u)) - 1u))) - 1u) & 31u);
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return 0;
+    // u coordinates: byte u lives at al[u]; al is the 8-byte aligned address at or before the first byte
+    const int32_t a0 = int32_t(reinterpret_cast<uintptr_t>(first_byte) & 7u);
+    uint8_t* al = first_byte - a0;
+    const int32_t s = int32_t(incl - len) + a0, e = s + int32_t(len), end_u = a0 + int32_t(total);
+    uint32_t* bm_s = reinterpret_cast<uint32_t*>(stage);          // the first 128 bytes double as the bitmap scratch
+    for (int32_t wb = 0; wb < end_u; wb += 1024) {                 // warp-uniform
+        // bitmap of token starts in the window + prefix counts: tokens that end at or before the window come first; then
+        // bit (start - wb) for every token in the window (one that began before it and reaches into it owns bit 0)
+        const int32_t wend = min(end_u, wb + 1024);
+        const uint32_t firstk = uint32_t(__popc(__ballot_sync(FULL, valid && e <= wb)));
+        bm_s[lane] = 0u;
+        __syncwarp();
+        if (valid && e > wb && s < wend) {
+            const uint32_t r = uint32_t(max(s, wb) - wb);
+            atomicOr(&bm_s[r >> 5], 1u << (r & 31u));
+        }
+        __syncwarp();
+        const uint32_t bm = bm_s[lane];
+        __syncwarp();
+        uint32_t pre;
+        {
+            const uint32_t pc = uint32_t(__popc(bm));
+            uint32_t inc = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += up;
+            }
+            pre = inc - pc;
+        }
+        for (int32_t cb = wb; cb < wend; cb += kChunk) {           // warp-uniform
+            const int32_t clim = min(wend, cb + kChunk);
+            const int32_t front = max(cb, a0);                     // sources below this are finished output in global memory
+            uint32_t val[kSteps];
+            uint32_t near_mask = 0u, far_mask = 0u;                // bit i: val[i] is a position on the stage / in front of it, not a byte
+            // ---- pass 1: resolve ... -------------------------------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < kSteps; ++i) {
+                const int32_t base = cb + 32 * i;
+                val[i] = 0u;
+                if (base < clim) {                                 // warp-uniform
+                    const int32_t x = base + lane;
+                    const int32_t lim = max(base, a0);             // first byte of the step inside the queue
+                    const uint32_t m = __shfl_sync(FULL, bm, (base - wb) >> 5), p = __shfl_sync(FULL, pre, (base - wb) >> 5);
+                    int k = int((firstk + p + uint32_t(__popc(m & ((2u << lane) - 1u))) - 1u) & 31u);
+                    uint32_t tk = __shfl_sync(FULL, t, k);
+                    int32_t sk = __shfl_sync(FULL, s, k);
+                    const bool mine = x >= a0 && x < end_u;
+                    const bool is_lit = !(tk >> 31);
+                    const int32_t d0 = int32_t(((tk >> 16) & 0x7fffu) + 1u);
+                    const int32_t y0 = x - d0;
+                    // the common case without a branch: a literal, or a match whose source lies in front of the step and of
+                    // the match itself
+                    const bool slow = mine && !is_lit && y0 >= min(sk, lim);
+                    val[i] = is_lit ? (tk & 0xffu) : uint32_t(y0 - cb);
+                    const uint32_t bit = (mine && !is_lit && !slow) ? (1u << i) : 0u;
+                    far_mask |= y0 < front ? bit : 0u;
+                    near_mask |= y0 < front ? 0u : bit;
+                    if (__any_sync(FULL, slow)) {
+                        // rare: the match overlaps itself (dist < len: same phase, in front of it), or its source lies inside
+                        // this step's 32 bytes and is chased through its own owner token
+                        int32_t xx = x;
+                        bool need = slow;
+                        for (;;) {
+                            if (need) {
+                                if (!(tk >> 31)) { val[i] = tk & 0xffu; need = false; }
+                                else {
+                                    const int32_t d = int32_t(((tk >> 16) & 0x7fffu) + 1u);
+                                    int32_t y = xx - d;
+                                    if (y >= sk) y = sk - d + (xx - sk) % d;
+                                    if (y < lim) {
+                                        val[i] = uint32_t(y - cb);
+                                        if (y < front) far_mask |= 1u << i; else near_mask |= 1u << i;
+                                        need = false;
+                                    } else xx = y;
+                                }
+                            }
+                            if (!__any_sync(FULL, need)) break;
+                            const uint32_t r = uint32_t((need ? xx : lim) - wb);
+                            const uint32_t m2 = __shfl_sync(FULL, bm, int(r >> 5)), p2 = __shfl_sync(FULL, pre, int(r >> 5));
+                            k = int((firstk + p2 + uint32_t(__popc(m2 & ((2u << (r & 31u)) - 1u))) - 1u) & 31u);
+                            tk = __shfl_sync(FULL, t, k);
+                            sk = __shfl_sync(FULL, s, k);
+                        }
+                    }
+                }
+            }
+            // ... and issue the loads of the sources in front of the chunk, back to back (no control flow between them: a
+            // load inside the resolve loop was waited for at the next step's first branch)
+#pragma unroll
+            for (int i = 0; i < kSteps; ++i)
+                if ((far_mask >> i) & 1u) val[i] = __ldcg(al + cb + int32_t(val[i]));     // L2 only: L1 stays with the decode lanes
+            // ---- pass 2: in order through the stage ------------------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < kSteps; ++i) {
+                const int32_t base = cb + 32 * i;
+                if (base < clim) {                                 // warp-uniform
+                    const int32_t x = base + lane;
+                    uint32_t v = val[i];
+                    if ((near_mask >> i) & 1u) v = stage[v];
+                    if (x >= a0 && x < end_u) stage[x - cb] = uint8_t(v);
+                    __syncwarp();
+                }
+            }
+            // ---- pass 3: the chunk goes out: whole 8-byte words one per lane, the partial first / last word of the queue
+            // byte by byte on lanes 0-7 / 8-15 -----------------------------------------------------------------------------------
+            {
+                const int32_t lo = cb + 8 * lane;
+                if (lo >= front && lo + 8 <= clim) *reinterpret_cast<uint2*>(al + lo) = *reinterpret_cast<const uint2*>(stage + 8 * lane);
+                const int32_t hw = front & ~7, tw = clim & ~7;
+                const int32_t u = lane < 8 ? hw + lane : tw + (lane - 8);
+                const int32_t w = u & ~7;
+                if (lane < 16 && (lane < 8 || tw != hw) && u >= front && u < clim && !(w >= front && w + 8 <= clim)) al[u] = stage[u - cb];
+            }
+            __syncwarp();                                          // the stage is reused; the stores are visible to the next loads
+        }
+    }
+    return total;
 }
 
 __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock* __restrict__ blocks, int n_blocks,
@@ -247,13 +347,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                 const bool any = __any_sync(FULL, nq > 0);
                 if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
             } else if (r > 0) {
-                // ---- the queues of the previous round -> bytes: this warp's four streams, interleaved ----------------------------
+                // ---- the queues of the previous round -> bytes: this warp's four streams, one after the other -----------------
                 const int pb = buf ^ 1;
                 const int cw = wid - kWsDecWarps;
-                uint32_t* bm_s = ctl.bitmap[cw];
-                CopyQueue Q[kQpw];
-                int32_t max_end = 0;
-#pragma unroll
+                uint8_t* stage = ctl.stage[cw];
                 for (int j = 0; j < kQpw; ++j) {
                     const int k = cw * kQpw + j;
                     int nq = int(ctl.qn[pb][k]);
@@ -268,76 +365,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         if (lane == 0) ctl.pos[k] = pos + len;
                         nq = 0;
                     }
-                    const bool valid = lane < nq;
-                    Q[j].t = valid ? q[lane] : 0u;
-                    const uint32_t len = (Q[j].t >> 31) ? (Q[j].t & 0x1ffu) : (valid ? 1u : 0u);
-                    uint32_t incl = len;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    const uint32_t total = __shfl_sync(FULL, incl, 31);
-                    uint8_t* first_byte = out + pos;
-                    Q[j].a0 = int32_t(reinterpret_cast<uintptr_t>(first_byte) & 3u);
-                    Q[j].al = first_byte - Q[j].a0;
-                    Q[j].s = int32_t(incl - len) + Q[j].a0;
-                    Q[j].e = Q[j].s + int32_t(len);
-                    Q[j].end_u = total ? Q[j].a0 + int32_t(total) : 0;
-                    Q[j].bm = Q[j].pre = Q[j].firstk = 0u;
-                    max_end = max(max_end, Q[j].end_u);
-                    if (lane == 0 && total) ctl.pos[k] = pos + total;
-                }
-                for (int32_t wb = 0; wb < max_end; wb += 1024) {                   // warp-uniform
-#pragma unroll
-                    for (int j = 0; j < kQpw; ++j)
-                        if (wb < Q[j].end_u) copy_window(Q[j], wb, lane, bm_s);
-                    const int32_t wlim = min(max_end, wb + 1024);
-                    for (int32_t base = wb; base < wlim; base += 32) {
-                        const int32_t x = base + lane;
-                        uint32_t val[kQpw];
-                        int32_t src[kQpw];
-                        uint32_t load_mask = 0u, store_mask = 0u;
-                        // resolve the byte of every queue and issue its load ...
-#pragma unroll
-                        for (int j = 0; j < kQpw; ++j) {
-                            val[j] = 0u; src[j] = 0;
-                            if (base >= Q[j].end_u) continue;                     // warp-uniform
-                            const int32_t lim = max(base, Q[j].a0);              // first byte of the step inside the queue
-                            const bool mine = x >= Q[j].a0 && x < Q[j].end_u;
-                            const uint32_t m = __shfl_sync(FULL, Q[j].bm, (base - wb) >> 5), p = __shfl_sync(FULL, Q[j].pre, (base - wb) >> 5);
-                            const int k = int((Q[j].firstk + p + uint32_t(__popc(m & ((2u << lane) - 1u))) - 1u) & 31u);
-                            uint32_t tk = __shfl_sync(FULL, Q[j].t, k);
-                            int32_t sk = __shfl_sync(FULL, Q[j].s, k);
-                            int32_t xx = x;
-                            bool need = mine;
-                            for (;;) {
-                                if (need) {
-                                    if (!(tk >> 31)) { val[j] = tk & 0xffu; need = false; }
-                                    else {
-                                        const int32_t d = int32_t(((tk >> 16) & 0x7fffu) + 1u);
-                                        int32_t y = xx - d;
-                                        if (y >= sk) y = sk - d + (xx - sk) % d;  // the match overlaps itself: same phase, in front of it
-                                        if (y < lim) { src[j] = y; load_mask |= 1u << j; need = false; }
-                                        else xx = y;
-                                    }
-                                }
-                                if (!__any_sync(FULL, need)) break;
-                                // rare: a source inside this step's 32 bytes: chase it through its own owner token
-                                const int k2 = copy_owner(Q[j], need ? xx : lim, wb);
-                                tk = __shfl_sync(FULL, Q[j].t, k2);
-                                sk = __shfl_sync(FULL, Q[j].s, k2);
-                            }
-                            if (mine) store_mask |= 1u << j;
-                        }
-#pragma unroll
-                        for (int j = 0; j < kQpw; ++j)
-                            if ((load_mask >> j) & 1u) val[j] = __ldcg(Q[j].al + src[j]);     // L2 only: L1 stays with the decode lanes
-                        // ... then store them
-#pragma unroll
-                        for (int j = 0; j < kQpw; ++j)
-                            if ((store_mask >> j) & 1u) Q[j].al[x] = uint8_t(val[j]);
-                        __syncwarp();                                              // visible to the next step's loads
+                    if (nq > 0) {                                                  // warp-uniform
+                        const uint32_t total = materialise(q, nq, out + pos, lane, stage);
+                        if (lane == 0) ctl.pos[k] = pos + total;
                     }
                 }
             }

@@ -41,8 +41,8 @@ constexpr uint32_t kLitUnset = kNonLit | (kClsOther << kClsShift);      // class
 // Second-level entries for literal/length codes of 11-15 bits.  Codes are canonical, so the long codes of a block are
 // sorted by length and share consecutive 10-bit prefixes: every prefix whose codes all have one length needs exactly as
 // many entries as it has codes, and only the (at most four) prefixes in which the length changes waste any - zlib's
-// `enough 288 10 15` gives 1334 entries for both levels, i.e. 310 here.  An overflow is reported as a corrupt block.
-constexpr int kLitSub = 320;
+// `enough 288 10 15` gives 1334 entries for both levels, i.e. 310 here (312 with padding).  An overflow is reported as a corrupt block.
+constexpr int kLitSub = 312;
 constexpr uint32_t kDistBad = 0x400u;
 
 BSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -103,9 +103,16 @@ struct BitReader {
         a0 = rf ? b0 : a0; a1 = rf ? b1 : a1;
         b0 = rf ? p0 : b0; b1 = rf ? p1 : b1;
 #if defined(__CUDA_ARCH__)
+#if defined(BSG_L1P)
+        asm volatile("{ .reg .pred p, q; .reg .b32 t; setp.ne.u32 p, %3, 0; @p ld.global.v2.u32 {%0, %1}, [%2];\n\t"
+                     "and.b32 t, %4, 15; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L2 [%2 + 256];\n\t"
+                     "and.b32 t, %4, 3; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L1 [%2 + 64]; }"
+                     : "+r"(p0), "+r"(p1) : "l"(base + wi), "r"(uint32_t(rf)), "r"(wi) : "memory");
+#else
         asm volatile("{ .reg .pred p, q; .reg .b32 t; setp.ne.u32 p, %3, 0; @p ld.global.v2.u32 {%0, %1}, [%2];\n\t"
                      "and.b32 t, %4, 15; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L2 [%2 + 256]; }"
                      : "+r"(p0), "+r"(p1) : "l"(base + wi), "r"(uint32_t(rf)), "r"(wi) : "memory");
+#endif
 #else
         if (rf) ld2(base + wi, p0, p1);
 #endif

@@ -58,8 +58,11 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
         }
         if (nq > 0) {
             // the kernel's byte-parallel materialisation (inflate.cu: materialise), lane by lane: token starts in a
-            // bitmap (1024-byte windows), owner of a byte = prefix pop-count, sources inside the window are chased
-            // through their owner tokens, sources before it are read from finished output
+            // bitmap (1024-byte windows), owner of a byte = prefix pop-count; the output is built in chunks of 256 bytes:
+            // pass 1 resolves every byte of the chunk to a literal, a source in FRONT of the chunk (finished output, loaded
+            // before anything of the chunk is written) or a source inside the chunk (sources inside the byte's own 32-byte
+            // step are chased through their owner tokens); pass 2 goes through the steps in order via the stage; pass 3
+            // copies the stage out
             uint32_t t[32], incl[32]; int32_t s[32], e[32];
             uint32_t run = 0;
             for (int lane = 0; lane < 32; ++lane) {
@@ -70,14 +73,14 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
             }
             const uint32_t total = run;
             uint8_t* first_byte = out + pos_base;
-            const uint32_t a0 = uint32_t(reinterpret_cast<uintptr_t>(first_byte) & 3u);
+            const uint32_t a0 = uint32_t(reinterpret_cast<uintptr_t>(first_byte) & 7u);
             uint8_t* al = first_byte - a0;
             for (int lane = 0; lane < 32; ++lane) {
                 const uint32_t len = lane < nq ? ((t[lane] >> 31) ? (t[lane] & 0x1ffu) : 1u) : 0u;
                 s[lane] = int32_t(incl[lane] - len + a0); e[lane] = s[lane] + int32_t(len);
             }
             const int32_t end_u = int32_t(a0 + total);
-            for (int32_t wb = 0; wb < end_u; wb += 1024) {
+            for (int32_t wb = 0; wb < end_u && total; wb += 1024) {
                 const int32_t wend = std::min(end_u, wb + 1024);
                 uint32_t firstk = 0, bm[32], pre[32];
                 for (int k = 0; k < 32; ++k) bm[k] = 0;
@@ -91,25 +94,36 @@ static int inflate_block(const uint8_t* buf, uint32_t in_off, uint32_t in_len, u
                 }
                 uint32_t acc = 0;
                 for (int k = 0; k < 32; ++k) { pre[k] = acc; acc += uint32_t(__builtin_popcount(bm[k])); }
-                for (int32_t base = wb; base < wend; base += 32) {      // one warp step: all its loads precede its stores
-                    const int32_t lim = std::max(base, int32_t(a0)), bend = std::min(wend, base + 32);
-                    uint8_t stage[128];
-                    for (int32_t u = lim; u < bend; ++u) {
+                for (int32_t cb = wb; cb < wend; cb += 256) {
+                    const int32_t clim = std::min(wend, cb + 256), front = std::max(cb, int32_t(a0));
+                    uint8_t stage[256];
+                    int32_t val[256]; uint8_t kind[256];            // kind: 0 literal byte, 1 source in front of the chunk, 2 on the stage
+                    for (int32_t u = front; u < clim; ++u) {        // pass 1 (every load happens before any store of the chunk)
+                        const int32_t lim = std::max(u & ~31, int32_t(a0));
                         int32_t xx = u;
                         for (int hops = 0;; ++hops) {
                             if (hops > 40) return 7;
                             const uint32_t r = uint32_t(xx - wb);
                             const int k = int((firstk + pre[r >> 5] + uint32_t(__builtin_popcount(bm[r >> 5] & ((2u << (r & 31u)) - 1u))) - 1u) & 31u);
                             if (!(xx >= s[k] && xx < e[k])) return 8;  // the owner lookup must land on the covering token
-                            if (!(t[k] >> 31)) { stage[u - base] = uint8_t(t[k]); break; }
+                            if (!(t[k] >> 31)) { val[u - cb] = int32_t(t[k] & 0xffu); kind[u - cb] = 0; break; }
                             const int32_t d = int32_t(((t[k] >> 16) & 0x7fffu) + 1u);
                             int32_t y = xx - d;
                             if (y >= s[k]) y = s[k] - d + (xx - s[k]) % d;
-                            if (y < lim) { stage[u - base] = al[y]; break; }
+                            if (y < lim) {
+                                if (y < front) { val[u - cb] = al[y]; kind[u - cb] = 1; }
+                                else { val[u - cb] = y - cb; kind[u - cb] = 2; }
+                                break;
+                            }
                             xx = y;
                         }
                     }
-                    for (int32_t u = lim; u < bend; ++u) al[u] = stage[u - base];
+                    for (int32_t u = front; u < clim; ++u)          // pass 2: a stage source was written by an earlier STEP
+                        if (kind[u - cb] == 2) {
+                            if (val[u - cb] + cb >= (u & ~31)) return 9;
+                            stage[u - cb] = stage[val[u - cb]];
+                        } else stage[u - cb] = uint8_t(val[u - cb]);
+                    for (int32_t u = front; u < clim; ++u) al[u] = stage[u - cb];      // pass 3
                 }
             }
             pos_base += total;

@@ -1083,7 +1083,9 @@ private:
         hi_prio_ = !keep_raw_;
         BSG_CUDA(cudaEventRecord(c.ev_order, c.s_comp));
         BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_order, 0));
-        std::vector<Span> inflate_spans, walk_spans, h2d_spans;
+        std::vector<Span> inflate_spans, walk_spans, h2d_spans, crc_spans;
+        const size_t dec_first = kt_.decode.size(), cnt_first = kt_.count.size();
+        const bool dbg_tl = getenv("BSG_DEBUG") != nullptr;
         double t_desc = 0, t_copy = 0, t_wait = 0, t_finish = 0;
         std::vector<InflateBlock> blocks;
         std::vector<uint32_t> crcs;
@@ -1264,8 +1266,11 @@ private:
                 // batch; the raw buffer is not recycled before it has finished (finish()).
                 BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
                 BSG_CUDA(cudaStreamWaitEvent(c.s_aux, c.ev_inflated[slot], 0));
+                Span spc{nullptr, nullptr};
+                if (dbg_tl) { spc = Span{c.timing_event(), c.timing_event()}; BSG_CUDA(cudaEventRecord(spc.a, c.s_aux)); }
                 launch_crc32(c.g_blocks[slot].as<InflateBlock>(), c.g_crc[slot].as<uint32_t>(), up.n_blocks, up.d_raw,
                              c.scalars.as<DeviceScalars>(), c.s_aux);
+                if (dbg_tl) { BSG_CUDA(cudaEventRecord(spc.b, c.s_aux)); crc_spans.push_back(spc); }
                 BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
                 kt_.launches += up.n_blocks ? 1 : 0;
             }
@@ -1278,12 +1283,13 @@ private:
             Span spw{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(spw.a, ws));
             launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, c.g_counts[slot].as<uint32_t>(),
-                        c.g_base[slot].as<uint32_t>(), c.g_total.as<uint32_t>() + slot, up.d_offs, up.end_pos,
+                        c.g_base[slot].as<uint32_t>(), c.h_total.as<uint32_t>() + slot, up.d_offs, up.end_pos,
                         c.scalars.as<DeviceScalars>(), ws);
             BSG_CUDA(cudaEventRecord(spw.b, ws));
             walk_spans.push_back(spw);
             kt_.launches += (up.n_blocks ? 1 : 0) + (up.n_walkers ? 3 : 1);
-            BSG_CUDA(cudaMemcpyAsync(c.h_total.as<uint32_t>() + slot, c.g_total.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ws));
+            // (the record count lands in pinned host memory straight from the scan kernel: a 4-byte cudaMemcpy would queue
+            // behind the 32 MiB result copies on the device-to-host engine - measured: up to 6 ms per batch)
             BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));
             nvtxRangePop();
         };
@@ -1314,8 +1320,7 @@ private:
                     // (Polling for the frontier between upload chunks instead of blocking here was measured: no gain.)
                     ReadTable t = table();
                     int32_t* f = c.h_front.as<int32_t>();
-                    BSG_CUDA(cudaMemcpyAsync(f, t.tid + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
-                    BSG_CUDA(cudaMemcpyAsync(f + 1, t.pos + (n_rows_ + n - 1), 4, cudaMemcpyDeviceToHost, c.s_hi));
+                    launch_publish_pair(t.tid + (n_rows_ + n - 1), t.pos + (n_rows_ + n - 1), f, c.s_hi);      // not a memcpy: see compute()
                     BSG_CUDA(cudaEventRecord(c.ev_front[0], c.s_hi));
                     BSG_CUDA(cudaEventSynchronize(c.ev_front[0]));
                     advance(n_rows_ + n, uint32_t(f[0]), f[1]);
@@ -1327,6 +1332,7 @@ private:
             nvtxRangePop();
         };
 
+        const double t_pipe0 = now_ms();
         if (nb > 0) upload(0);
         if (nb > 1) upload(1);
         if (nb > 0) compute(0);
@@ -1336,15 +1342,30 @@ private:
             const double tt = now_ms();
             finish(bi);
             t_finish += now_ms() - tt;
+            if (dbg_tl) fprintf(stderr, "[bsg]   host: finish(%zu) entered %.2f, returned %.2f ms after the pipeline started\n", bi, tt - t_pipe0, now_ms() - t_pipe0);
         }
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_hi));
         if (opts_.verify_crc) BSG_CUDA(cudaStreamSynchronize(c.s_aux));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);
         tm_.ms_h2d = sum_ms(h2d_spans);         // on the copy stream: the time the copy engine (and, when staging, the pool) needed
-        if (getenv("BSG_DEBUG"))
+        if (getenv("BSG_DEBUG")) {
             fprintf(stderr, "[bsg] gpu pipeline host ms: descriptors %.1f, slot wait %.1f, memcpy+h2d %.1f, finish(wait total) %.1f; device inflate %.1f, walk %.1f\n",
                     t_desc, t_wait, t_copy, t_finish, tm_.ms_inflate_gpu, sum_ms(walk_spans));
+            // device timeline of the batches relative to the first upload (ms): h2d, inflate, walk, decode
+            auto rel = [&](cudaEvent_t e) { float ms = 0; cudaEventElapsedTime(&ms, h2d_spans[0].a, e); return ms; };
+            for (size_t k = 0; k < nb && !h2d_spans.empty(); ++k) {
+                fprintf(stderr, "[bsg]   batch %zu: h2d %.2f-%.2f inflate %.2f-%.2f walk %.2f-%.2f", k, rel(h2d_spans[k].a), rel(h2d_spans[k].b),
+                        rel(inflate_spans[k].a), rel(inflate_spans[k].b), rel(walk_spans[k].a), rel(walk_spans[k].b));
+                if (!keep_raw_ && k < dec_first + nb && dec_first + k < kt_.decode.size())
+                    fprintf(stderr, " decode %.2f-%.2f", rel(kt_.decode[dec_first + k].a), rel(kt_.decode[dec_first + k].b));
+                if (k < crc_spans.size()) fprintf(stderr, " crc %.2f-%.2f", rel(crc_spans[k].a), rel(crc_spans[k].b));
+                fprintf(stderr, "\n");
+            }
+            for (size_t k = cnt_first; k < kt_.count.size(); ++k)
+                fprintf(stderr, "[bsg]   count launch %zu: join %.2f-%.2f count %.2f-%.2f\n", k - cnt_first, rel(kt_.join[k].a), rel(kt_.join[k].b),
+                        rel(kt_.count[k].a), rel(kt_.count[k].b));
+        }
         BSG_CUDA(cudaMemcpyAsync(c.h_scalars.p, c.scalars.p, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         check_status(c.h_scalars.as<DeviceScalars>()->status);

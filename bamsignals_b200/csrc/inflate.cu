@@ -518,8 +518,9 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        *total = s_carry;
         if (offs) offs[s_carry] = end_pos;
+        *total = s_carry;                 // may be pinned host memory (the streaming pipeline reads it after an event)
+        __threadfence_system();
     }
 }
 
@@ -541,6 +542,15 @@ void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d
 }
 
 int inflate_wave_blocks(int n_sm) { return n_sm * kWsStreams; }
+
+namespace {
+__global__ void k_publish_pair(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* dst) {
+    dst[0] = *a;
+    dst[1] = *b;
+    __threadfence_system();
+}
+}  // namespace
+void launch_publish_pair(const int32_t* d_a, const int32_t* d_b, int32_t* dst, cudaStream_t s) { k_publish_pair<<<1, 1, 0, s>>>(d_a, d_b, dst); }
 
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s) {

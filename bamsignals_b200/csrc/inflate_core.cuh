@@ -103,16 +103,10 @@ struct BitReader {
         a0 = rf ? b0 : a0; a1 = rf ? b1 : a1;
         b0 = rf ? p0 : b0; b1 = rf ? p1 : b1;
 #if defined(__CUDA_ARCH__)
-#if defined(BSG_L1P)
-        asm volatile("{ .reg .pred p, q; .reg .b32 t; setp.ne.u32 p, %3, 0; @p ld.global.v2.u32 {%0, %1}, [%2];\n\t"
-                     "and.b32 t, %4, 15; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L2 [%2 + 256];\n\t"
-                     "and.b32 t, %4, 3; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L1 [%2 + 64]; }"
-                     : "+r"(p0), "+r"(p1) : "l"(base + wi), "r"(uint32_t(rf)), "r"(wi) : "memory");
-#else
         asm volatile("{ .reg .pred p, q; .reg .b32 t; setp.ne.u32 p, %3, 0; @p ld.global.v2.u32 {%0, %1}, [%2];\n\t"
                      "and.b32 t, %4, 15; setp.eq.and.u32 q, t, 0, p; @q prefetch.global.L2 [%2 + 256]; }"
                      : "+r"(p0), "+r"(p1) : "l"(base + wi), "r"(uint32_t(rf)), "r"(wi) : "memory");
-#endif
+        // (measured and dropped: also asking L1 for the sector 64 bytes ahead - 8.56 vs 8.52 ms, no gain)
 #else
         if (rf) ld2(base + wi, p0, p1);
 #endif

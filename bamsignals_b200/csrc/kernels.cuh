@@ -97,6 +97,11 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
                  uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
 
+// dst[0] = *d_a, dst[1] = *d_b by a one-thread kernel; dst may be pinned host memory.  (Control values of the streaming
+// pipeline - a batch's record count, the (tid, pos) frontier - must not travel as cudaMemcpy: a 4-byte copy queues behind
+// the 32 MiB result copies on the device-to-host copy engine.)
+void launch_publish_pair(const int32_t* d_a, const int32_t* d_b, int32_t* dst, cudaStream_t s);
+
 // K3: per tile, binary-search the (tid,pos)-sorted table for the candidate row range (the job of the sort + chunk
 // + sweep in overlapAndPileup, src/bamsignals.cpp:246-285).
 void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s);

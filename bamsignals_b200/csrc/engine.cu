@@ -52,6 +52,7 @@ constexpr uint64_t kSpanGap = 160u << 10;       // file gaps up to this many byt
 constexpr uint64_t kSmallJobBytes = 16u << 20;   // inflated bytes up to which the default path inflates on the host
 constexpr int kMinRecord = 36;                  // block_size + 32-byte fixed part: smallest possible record
 constexpr int64_t kD2HChunk = 32ll << 20;       // bytes per pinned result-staging buffer
+constexpr int64_t kPackMinInts = 1ll << 16;     // result portions from this size on cross PCIe as bytes (opts.result_pack)
 constexpr int kOutSlots = 3;                    // pinned result-staging ring
 constexpr int kUp = 4;                          // GPU-inflate path: upload ring (compressed bytes + descriptors); raw buffers: 2
 
@@ -89,7 +90,7 @@ struct DeviceCtx {
     int dev = 0;
     int n_sm = 148;
     bool init = false;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr, s_hi = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_walk = nullptr, s_d2h = nullptr, s_hi = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
@@ -100,7 +101,8 @@ struct DeviceCtx {
     DevBuf g_comp[kUp], g_blocks[kUp], g_crc[kUp], g_walkers[kUp], g_counts[kUp], g_base[kUp], g_raw[2], g_offs[2], g_total;
     PinBuf h_total, h_desc[kUp];
     cudaEvent_t ev_pin[kSlots] = {}, ev_up[kUp] = {}, ev_total[kUp] = {}, ev_inflated[kUp] = {}, ev_crc[kUp] = {}, ev_gfree[2] = {};
-    PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front;
+    PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front, h_ovf[kOutSlots], h_pack_cnt;
+    DevBuf g_pack[kOutSlots], g_pack_cnt;       // result narrowing (opts.result_pack): packed bytes per ring slot, overflow counters
     cudaEvent_t ev_d2h[kOutSlots] = {}, ev_front[2] = {}, ev_order = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
@@ -113,6 +115,7 @@ struct DeviceCtx {
         BSG_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_walk, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
         {   // decode + count kernels of finished batches overtake the inflate of the next one
             int lo_p = 0, hi_p = 0;
@@ -161,7 +164,8 @@ struct DeviceCtx {
         for (auto& b : tab) b.release();
         c0.release(); c1.release(); tiles_i32.release(); tiles_i64.release(); out.release(); scalars.release();
         h_scalars.release();
-        for (int i = 0; i < kOutSlots; ++i) { h_out[i].release(); cudaEventDestroy(ev_d2h[i]); }
+        for (int i = 0; i < kOutSlots; ++i) { h_out[i].release(); h_ovf[i].release(); g_pack[i].release(); cudaEventDestroy(ev_d2h[i]); }
+        h_pack_cnt.release(); g_pack_cnt.release();
         h_tiles.release(); h_front.release();
         cudaEventDestroy(ev_front[0]); cudaEventDestroy(ev_front[1]);
         for (int i = 0; i < 2; ++i) { g_raw[i].release(); g_offs[i].release(); cudaEventDestroy(ev_gfree[i]); }
@@ -174,7 +178,7 @@ struct DeviceCtx {
         g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
-        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_walk); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
         init = false;
     }
 };
@@ -779,6 +783,11 @@ private:
     void start_streamer() {
         DeviceCtx& c = *ctx_;
         for (int k = 0; k < kOutSlots; ++k) c.h_out[k].ensure(size_t(kD2HChunk));
+        if (opts_.result_pack >= 0) {
+            for (int k = 0; k < kOutSlots; ++k) c.g_pack[k].ensure(size_t(kD2HChunk / 4));
+            c.h_pack_cnt.ensure(64);
+            if (!c.g_pack_cnt.p) { c.g_pack_cnt.ensure(64); BSG_CUDA(cudaMemset(c.g_pack_cnt.p, 0, 64)); }
+        }
         os_stop_ = false; os_abort_ = false;
         os_jobs_.clear();
         os_err_ = Error{0, ""};
@@ -817,10 +826,27 @@ private:
             }
             const int np = int(cut.size()) - 1;
             cudaError_t e = cudaStreamWaitEvent(c.s_d2h, job.computed, 0);
+            // A large portion crosses PCIe as ONE BYTE per element (+ the few elements above 254 as (index, value) pairs
+            // written straight into pinned host memory): C2's 1.6 GB of int32 counts - more than its 1.2 GB of compressed
+            // input - took 68 ms at the 23 GB/s the device-to-host path reaches next to the upload, longer than the whole
+            // fetch pipeline.  The scatter below widens the bytes while it moves them.
+            const int pack_div = opts_.result_pack < 0 ? 0 : (opts_.result_pack == 0 ? 64 : std::max(2, opts_.result_pack));
+            std::vector<uint32_t> ovf_cap(size_t(np), 0u);          // 0 = this piece travels as int32
             auto issue = [&](int k) {
                 const int slot = k % kOutSlots;
                 const int64_t ints = tile_dev_off_[cut[k + 1]] - tile_dev_off_[cut[k]];
-                cudaError_t r = cudaMemcpyAsync(c.h_out[slot].p, c.out.as<int32_t>() + tile_dev_off_[cut[k]], size_t(ints) * 4, cudaMemcpyDeviceToHost, c.s_d2h);
+                const int32_t* src = c.out.as<int32_t>() + tile_dev_off_[cut[k]];
+                cudaError_t r = cudaSuccess;
+                if (pack_div > 0 && ints >= kPackMinInts && ints <= kD2HChunk / 4) {
+                    const uint32_t cap = uint32_t(std::max<int64_t>(1024, ints / pack_div));
+                    try { c.h_ovf[slot].ensure(size_t(cap) * sizeof(uint2)); } catch (const Error&) { return cudaErrorMemoryAllocation; }
+                    ovf_cap[size_t(k)] = cap;
+                    launch_pack_u8(src, ints, c.g_pack[slot].as<uint8_t>(), c.h_ovf[slot].as<uint2>(), cap, c.g_pack_cnt.as<uint32_t>() + slot, c.s_d2h);
+                    launch_publish_reset(c.g_pack_cnt.as<uint32_t>() + slot, c.h_pack_cnt.as<uint32_t>() + slot, c.s_d2h);
+                    r = cudaMemcpyAsync(c.h_out[slot].p, c.g_pack[slot].p, size_t(ints), cudaMemcpyDeviceToHost, c.s_d2h);
+                } else {
+                    r = cudaMemcpyAsync(c.h_out[slot].p, src, size_t(ints) * 4, cudaMemcpyDeviceToHost, c.s_d2h);
+                }
                 if (r == cudaSuccess) r = cudaEventRecord(c.ev_d2h[slot], c.s_d2h);
                 return r;
             };
@@ -828,18 +854,56 @@ private:
             for (int k = 0; k < np && e == cudaSuccess; ++k) {
                 if (k + kOutSlots - 1 < np) e = issue(k + kOutSlots - 1);      // its slot was scattered in iteration k-1
                 if (e != cudaSuccess) break;
-                e = cudaEventSynchronize(c.ev_d2h[k % kOutSlots]);
+                const int slot = k % kOutSlots;
+                e = cudaEventSynchronize(c.ev_d2h[slot]);
                 if (e != cudaSuccess) break;
-                const int32_t* src = c.h_out[k % kOutSlots].as<int32_t>();
                 const int64_t t_lo = cut[k], base = tile_dev_off_[t_lo], n = cut[k + 1] - t_lo;
-                const int64_t grain = std::max<int64_t>(1, n / (int64_t(pool_->size()) * 4));
-                pool_->parallel_for(n, grain, [&](int64_t a, int64_t b, int) {
-                    for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
-                        int32_t* dst = cnt_.out ? cnt_.out + ht_.out_off[t]
-                                                : (cnt_.out_ptrs[ht_.region[t]] ? cnt_.out_ptrs[ht_.region[t]] + (ht_.out_off[t] - cnt_.out_offsets[ht_.region[t]]) : nullptr);
-                        if (dst) memcpy(dst, src + (tile_dev_off_[t] - base), size_t(ht_.ints[t]) * 4);
+                uint32_t n_ovf = 0;
+                bool packed = ovf_cap[size_t(k)] != 0;
+                if (packed) {
+                    n_ovf = c.h_pack_cnt.as<uint32_t>()[slot];
+                    if (n_ovf > ovf_cap[size_t(k)]) {
+                        // too many large elements for the list: this piece travels again, as int32 (the copies already queued
+                        // for the next pieces go first; it is the rare case)
+                        e = cudaMemcpyAsync(c.h_out[slot].p, c.out.as<int32_t>() + base, size_t(tile_dev_off_[cut[k + 1]] - base) * 4,
+                                            cudaMemcpyDeviceToHost, c.s_d2h);
+                        if (e == cudaSuccess) e = cudaStreamSynchronize(c.s_d2h);
+                        if (e != cudaSuccess) break;
+                        packed = false;
                     }
-                });
+                }
+                auto dst_of = [&](int64_t t) -> int32_t* {
+                    return cnt_.out ? cnt_.out + ht_.out_off[t]
+                                    : (cnt_.out_ptrs[ht_.region[t]] ? cnt_.out_ptrs[ht_.region[t]] + (ht_.out_off[t] - cnt_.out_offsets[ht_.region[t]]) : nullptr);
+                };
+                const int64_t grain = std::max<int64_t>(1, n / (int64_t(pool_->size()) * 4));
+                if (packed) {
+                    const uint8_t* src = c.h_out[slot].as<uint8_t>();
+                    pool_->parallel_for(n, grain, [&](int64_t a, int64_t b, int) {
+                        for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
+                            int32_t* dst = dst_of(t);
+                            if (!dst) continue;
+                            const uint8_t* sp = src + (tile_dev_off_[t] - base);
+                            const int64_t m = ht_.ints[t];
+                            for (int64_t i = 0; i < m; ++i) dst[i] = int32_t(sp[i]);
+                        }
+                    });
+                    const uint2* ov = c.h_ovf[slot].as<uint2>();
+                    for (uint32_t j = 0; j < n_ovf; ++j) {          // the elements above 254, exactly
+                        const int64_t pos = base + int64_t(ov[j].x);
+                        const int64_t t = (std::upper_bound(tile_dev_off_.begin() + t_lo, tile_dev_off_.begin() + t_lo + n + 1, pos) - tile_dev_off_.begin()) - 1;
+                        int32_t* dst = dst_of(t);
+                        if (dst) dst[pos - tile_dev_off_[t]] = int32_t(ov[j].y);
+                    }
+                } else {
+                    const int32_t* src = c.h_out[slot].as<int32_t>();
+                    pool_->parallel_for(n, grain, [&](int64_t a, int64_t b, int) {
+                        for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
+                            int32_t* dst = dst_of(t);
+                            if (dst) memcpy(dst, src + (tile_dev_off_[t] - base), size_t(ht_.ints[t]) * 4);
+                        }
+                    });
+                }
             }
             if (e != cudaSuccess) {
                 std::lock_guard<std::mutex> g(os_m_);
@@ -1261,10 +1325,12 @@ private:
             BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
             launch_inflate(c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, c.g_comp[slot].as<uint8_t>(), up.d_raw,
                            c.scalars.as<DeviceScalars>(), c.s_comp);
+            BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
+            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
+            inflate_spans.push_back(sp);
             if (opts_.verify_crc) {
-                // integrity check on a side stream: it only reads the inflated bytes, so it overlaps walk + decode of this
-                // batch; the raw buffer is not recycled before it has finished (finish()).
-                BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
+                // integrity check on a side stream: it only reads the inflated bytes; the raw buffer is not recycled before
+                // it has finished (finish()).
                 BSG_CUDA(cudaStreamWaitEvent(c.s_aux, c.ev_inflated[slot], 0));
                 Span spc{nullptr, nullptr};
                 if (dbg_tl) { spc = Span{c.timing_event(), c.timing_event()}; BSG_CUDA(cudaEventRecord(spc.a, c.s_aux)); }
@@ -1274,12 +1340,13 @@ private:
                 BSG_CUDA(cudaEventRecord(c.ev_crc[slot], c.s_aux));
                 kt_.launches += up.n_blocks ? 1 : 0;
             }
-            BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
-            inflate_spans.push_back(sp);
-            // The record walk stays on the compute stream, between this batch's inflate and the next one's.  (Measured:
-            // on the high-priority stream its three small kernels cannot start while the next inflate holds every SM -
-            // C2 143 -> 181 ms.)
-            cudaStream_t ws = c.s_comp;
+            // The record walk has its own stream too.  Neither it nor the CRC kernel uses shared memory, and the inflate
+            // kernel leaves 2 KB of every SM free: their CTAs run NEXT TO the persistent inflate CTAs of the following batch,
+            // which is queued right behind this batch's inflate.  (Round 1: walk between two inflates on the compute stream,
+            // 1.3 ms of every 5.7 ms batch period with the SMs nearly idle; on another stream it could not start at all while
+            // an inflate launch held every SM.)
+            cudaStream_t ws = c.s_walk;
+            BSG_CUDA(cudaStreamWaitEvent(ws, c.ev_inflated[slot], 0));
             Span spw{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(spw.a, ws));
             launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, c.g_counts[slot].as<uint32_t>(),
@@ -1345,6 +1412,7 @@ private:
             if (dbg_tl) fprintf(stderr, "[bsg]   host: finish(%zu) entered %.2f, returned %.2f ms after the pipeline started\n", bi, tt - t_pipe0, now_ms() - t_pipe0);
         }
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
+        BSG_CUDA(cudaStreamSynchronize(c.s_walk));
         BSG_CUDA(cudaStreamSynchronize(c.s_hi));
         if (opts_.verify_crc) BSG_CUDA(cudaStreamSynchronize(c.s_aux));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);

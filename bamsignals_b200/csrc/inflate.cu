@@ -42,15 +42,19 @@ struct WsStream {
     uint32_t q[2][inflate_core::kQueue];             // token queues of the round being decoded / being materialised
 };
 struct WsCtl {
-    uint32_t qn[2][kWsStreams];                      // tokens in q[buf] of every stream
+    uint8_t qn[2][kWsStreams];                       // tokens in q[buf] of every stream (<= 32)
     uint32_t pos[kWsStreams];                        // bytes materialised so far (owned by the stream's copy warp)
-    uint32_t out_off[kWsStreams], out_len[kWsStreams];
+    uint32_t out_off[kWsStreams];
     uint32_t produced[2][kWsDecWarps];               // did the decode warp hand over anything in round buf?
     alignas(8) uint8_t stage[kWsCopyWarps][256];     // a copy warp's chunk of output being built (also its bitmap scratch)
 };
 constexpr size_t kWsSmem = sizeof(WsStream) * kWsStreams + sizeof(WsCtl);
-static_assert(sizeof(WsStream) % 8 == 0, "stream slots keep the tables aligned");
-static_assert(kWsSmem <= 227 * 1024, "one CTA per SM must fit the opt-in shared memory");
+static_assert(sizeof(WsStream) % 4 == 0 && (sizeof(WsStream) * kWsStreams) % 8 == 0, "stream slots keep queues and stage aligned");
+// One CTA per SM, and 2 KB less than the SM has (228 KB - 1 KB reserved per resident CTA): a CTA of a kernel WITHOUT shared
+// memory (record walk, CRC32, the one-thread publishers) then fits next to it, so those kernels of the batch before run
+// in the shadow of this one instead of between two launches (the launch is persistent and would otherwise own every SM
+// until it ends).
+static_assert(kWsSmem <= 226 * 1024, "leave room for a co-resident CTA without shared memory");
 static_assert(kWsCopyWarps * 4 == kWsStreams, "every copy warp owns four streams");
 
 // fill_queue's table lookups and queue stores through explicit shared-space addresses (kept in registers)
@@ -68,12 +72,6 @@ struct SmemAccess {
     }
     __device__ __forceinline__ void put(uint32_t byte_off, uint32_t v) const {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_a + byte_off), "r"(v) : "memory");
-    }
-    __device__ __forceinline__ uint32_t sub(uint32_t byte_off) const {
-        constexpr uint32_t off = offsetof(inflate_core::Tables, lit_sub);
-        uint32_t r;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(lit_a + off + byte_off) : "memory");
-        return r;
     }
     __device__ __forceinline__ uint32_t sub_if(bool take, uint32_t byte_off, uint32_t otherwise) const {     // predicated
         constexpr uint32_t off = offsetof(inflate_core::Tables, lit_sub);
@@ -290,7 +288,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
         if (is_dec) {
             fin = b0 + s >= n_blocks;
             if (!fin) { blk = blocks[b0 + s]; br.init(br.base, blk.in_off); }
-            ctl.out_off[s] = blk.out_off; ctl.out_len[s] = blk.out_len; ctl.pos[s] = 0;
+            ctl.out_off[s] = blk.out_off; ctl.pos[s] = 0;
             ctl.qn[0][s] = 0; ctl.qn[1][s] = 0;
             acc.lit_a = uint32_t(__cvta_generic_to_shared(S[s].T.lit));
             // identity shuffle: ptxas cannot re-derive the value from %tid inside the decode loop (it otherwise rebuilds
@@ -343,7 +341,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         fin = true;
                     }
                 }
-                ctl.qn[buf][s] = uint32_t(nq);
+                ctl.qn[buf][s] = uint8_t(nq);
                 const bool any = __any_sync(FULL, nq > 0);
                 if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
             } else if (r > 0) {
@@ -378,7 +376,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
             if (!more) break;                        // nothing was handed over in round r: round r - 1 was the last one
         }
         // every stream must have produced exactly ISIZE bytes
-        if (threadIdx.x < kWsStreams && b0 + s < n_blocks && ctl.pos[s] != ctl.out_len[s]) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
+        if (threadIdx.x < kWsStreams && b0 + s < n_blocks && ctl.pos[s] != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
         __syncthreads();                             // the next generation re-initialises the control block
     }
 }
@@ -411,20 +409,21 @@ __constant__ uint32_t c_x2n[20] = {0x40000000u, 0x20000000u, 0x08000000u, 0x0080
                                    0xa06a2517u, 0xed627daeu, 0x88d14467u, 0xd7bbfe6au, 0xec447f11u, 0x8e7ea170u, 0x6427800eu,
                                    0x4d47bae0u, 0x09fe548fu, 0x83852d0fu, 0x30362f1au, 0x7b5a9cc3u, 0x31fec169u};
 
+// slicing-by-4 tables in GLOBAL memory (4 KB, L1-resident): the kernel uses no shared memory, so that its CTAs fit next to
+// the persistent inflate CTA of the following batch
+__device__ uint32_t g_crc_tab[4][256];
+__global__ void k_crc_init() {
+    const int i = threadIdx.x;
+    uint32_t c = uint32_t(i);
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? kCrcPoly ^ (c >> 1) : c >> 1;
+    g_crc_tab[0][i] = c;
+    __syncthreads();
+    for (int t = 1; t < 4; ++t) { c = g_crc_tab[0][c & 0xffu] ^ (c >> 8); g_crc_tab[t][i] = c; }
+}
+
 __global__ void __launch_bounds__(kCrcWarps * 32) k_crc32(const InflateBlock* __restrict__ blocks, const uint32_t* __restrict__ want, int n_blocks,
                                                           const uint8_t* __restrict__ raw, DeviceScalars* sc) {
-    __shared__ uint32_t tab[4][256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t c = uint32_t(i);
-        for (int k = 0; k < 8; ++k) c = (c & 1u) ? kCrcPoly ^ (c >> 1) : c >> 1;
-        tab[0][i] = c;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t c = tab[0][i];
-        for (int t = 1; t < 4; ++t) { c = tab[0][c & 0xffu] ^ (c >> 8); tab[t][i] = c; }
-    }
-    __syncthreads();
+    const uint32_t (*tab)[256] = g_crc_tab;
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * kCrcWarps + (threadIdx.x >> 5);
     if (b >= n_blocks) return;
@@ -436,14 +435,14 @@ __global__ void __launch_bounds__(kCrcWarps * 32) k_crc32(const InflateBlock* __
     uint32_t n = lane == 0 ? head : seg;
     const uint8_t* p = raw + blk.out_off + beg;
     uint32_t crc = lane == 0 ? 0xffffffffu : 0u;
-    while (n && (reinterpret_cast<uintptr_t>(p) & 3)) { crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8); --n; }
+    while (n && (reinterpret_cast<uintptr_t>(p) & 3)) { crc = __ldg(&tab[0][(crc ^ *p++) & 0xffu]) ^ (crc >> 8); --n; }
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     for (; n >= 4; n -= 4) {
         crc ^= *w++;
-        crc = tab[3][crc & 0xffu] ^ tab[2][(crc >> 8) & 0xffu] ^ tab[1][(crc >> 16) & 0xffu] ^ tab[0][crc >> 24];
+        crc = __ldg(&tab[3][crc & 0xffu]) ^ __ldg(&tab[2][(crc >> 8) & 0xffu]) ^ __ldg(&tab[1][(crc >> 16) & 0xffu]) ^ __ldg(&tab[0][crc >> 24]);
     }
     p = reinterpret_cast<const uint8_t*>(w);
-    while (n--) crc = tab[0][(crc ^ *p++) & 0xffu] ^ (crc >> 8);
+    while (n--) crc = __ldg(&tab[0][(crc ^ *p++) & 0xffu]) ^ (crc >> 8);
     // fold: at level l the left partner is followed by 2^l pieces of seg bytes
     uint32_t X = 0x80000000u;                    // x^0
     for (uint32_t bits = 8u * seg, k = 0; bits; bits >>= 1, ++k)
@@ -491,35 +490,38 @@ __global__ void __launch_bounds__(128) k_walk(const uint8_t* __restrict__ raw, c
     if (bad) atomicOr(&sc->status, STATUS_CORRUPT);
 }
 
-// exclusive scan of counts[0..n) into base[0..n), total into *total and (when offs != null) the end sentinel
-__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict__ counts, int n, uint32_t* __restrict__ base,
-                                                      uint32_t* __restrict__ total, uint32_t* __restrict__ offs, uint32_t end_pos) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i0 = 0; i0 < n; i0 += 1024) {
-        const int i = i0 + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0u;
-        uint32_t incl = v;
+// exclusive scan of counts[0..n) into base[0..n), total into *total and (when offs != null) the end sentinel.
+// ONE warp, shuffles only: no shared memory and 32 threads, so that it fits next to a resident inflate CTA.
+__global__ void __launch_bounds__(32) k_scan_counts(const uint32_t* __restrict__ counts, int n, uint32_t* __restrict__ base,
+                                                    uint32_t* total, uint32_t* __restrict__ offs, uint32_t end_pos) {
+    const int lane = threadIdx.x;
+    uint32_t carry = 0;
+    for (int i0 = 0; i0 < n; i0 += 128) {                           // four counts per lane and step
+        const int i = i0 + 4 * lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 3 < n) v = *reinterpret_cast<const uint4*>(counts + i);
+        else {
+            if (i < n) v.x = counts[i];
+            if (i + 1 < n) v.y = counts[i + 1];
+            if (i + 2 < n) v.z = counts[i + 2];
+        }
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += up;
         }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        uint32_t pre = s_carry + incl - v;
-        for (int k = 0; k < wid; ++k) pre += s_warp[k];
+        const uint32_t pre = carry + incl - sum;
         if (i < n) base[i] = pre;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = pre + v;
-        __syncthreads();
+        if (i + 1 < n) base[i + 1] = pre + v.x;
+        if (i + 2 < n) base[i + 2] = pre + v.x + v.y;
+        if (i + 3 < n) base[i + 3] = pre + v.x + v.y + v.z;
+        carry += __shfl_sync(FULL, incl, 31);
     }
-    if (threadIdx.x == 0) {
-        if (offs) offs[s_carry] = end_pos;
-        *total = s_carry;                 // may be pinned host memory (the streaming pipeline reads it after an event)
+    if (lane == 0) {
+        if (offs) offs[carry] = end_pos;
+        *total = carry;                   // may be pinned host memory (the streaming pipeline reads it after an event)
         __threadfence_system();
     }
 }
@@ -555,18 +557,25 @@ void launch_publish_pair(const int32_t* d_a, const int32_t* d_b, int32_t* dst, c
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s) {
     if (n_blocks <= 0) return;
+    static thread_local bool have_tab[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || !have_tab[dev]) {
+        k_crc_init<<<1, 256, 0, s>>>();
+        if (dev >= 0 && dev < 16) have_tab[dev] = true;
+    }
     k_crc32<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
 }
 
 void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
                  uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s) {
     if (n_walkers <= 0) {
-        k_scan_counts<<<1, 1024, 0, s>>>(d_counts, 0, d_base, d_total, d_offs, end_pos);
+        k_scan_counts<<<1, 32, 0, s>>>(d_counts, 0, d_base, d_total, d_offs, end_pos);
         return;
     }
     const int grid = (n_walkers + 127) / 128;
     k_walk<false><<<grid, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_counts, nullptr, nullptr, sc);
-    k_scan_counts<<<1, 1024, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
+    k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
     k_walk<true><<<grid, 128, 0, s>>>(d_raw, d_walkers, n_walkers, nullptr, d_base, d_offs, sc);
 }
 

@@ -2,8 +2,9 @@
 // (tests/host_inflate_harness.cpp compiles this header with a plain C++ compiler).  Everything here is executed by ONE
 // thread per BGZF block: bit reader, decode-table construction, and Huffman symbols -> token queue.
 //
-// Shared-memory budget: 3304 bytes of tables per stream (16-bit entries; the distance table doubles as the code-length
-// scratch while a block header is parsed) + two 32-token queues = 3560 bytes, so that 64 streams fit one SM.
+// Shared-memory budget: 3284 bytes of tables per stream (16-bit entries; the distance table doubles as the code-length
+// scratch while a block header is parsed) + two 32-token queues = 3540 bytes, so that 64 streams and the copy warps'
+// stages fit one SM with 2 KB to spare (inflate.cu: a small kernel without shared memory can run next to the CTA).
 #pragma once
 #include <cstdint>
 
@@ -41,8 +42,8 @@ constexpr uint32_t kLitUnset = kNonLit | (kClsOther << kClsShift);      // class
 // Second-level entries for literal/length codes of 11-15 bits.  Codes are canonical, so the long codes of a block are
 // sorted by length and share consecutive 10-bit prefixes: every prefix whose codes all have one length needs exactly as
 // many entries as it has codes, and only the (at most four) prefixes in which the length changes waste any - zlib's
-// `enough 288 10 15` gives 1334 entries for both levels, i.e. 310 here (312 with padding).  An overflow is reported as a corrupt block.
-constexpr int kLitSub = 312;
+// `enough 288 10 15` gives 1334 entries for both levels, i.e. 310 here.  An overflow is reported as a corrupt block.
+constexpr int kLitSub = 310;
 constexpr uint32_t kDistBad = 0x400u;
 
 BSG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {

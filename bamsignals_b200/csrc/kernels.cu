@@ -529,6 +529,37 @@ __global__ void __launch_bounds__(kThreads) k_coverage(TileTable tiles, const in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Result narrowing (see kernels.cuh): four elements per thread, one 32-bit store; src is only 4-byte aligned.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_u8(const int32_t* __restrict__ src, int64_t n, uint8_t* __restrict__ dst, uint2* ovf,
+                                                 uint32_t cap, uint32_t* cnt) {
+    const int64_t i0 = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k;
+        if (i < n) {
+            const int32_t v = __ldcs(src + i);
+            uint32_t b = uint32_t(v);
+            if (uint32_t(v) > 254u) {                  // also negative values (none are produced; they would be kept exactly)
+                b = 255u;
+                const uint32_t slot = atomicAdd(cnt, 1u);
+                if (slot < cap) ovf[slot] = make_uint2(uint32_t(i), uint32_t(v));
+            }
+            word |= b << (8 * k);
+        }
+    }
+    if (i0 + 3 < n) *reinterpret_cast<uint32_t*>(dst + i0) = word;
+    else for (int k = 0; k < 4 && i0 + k < n; ++k) dst[i0 + k] = uint8_t(word >> (8 * k));
+}
+__global__ void k_publish_reset(uint32_t* cnt, uint32_t* host_cnt) {
+    *host_cnt = *cnt;
+    *cnt = 0u;
+    __threadfence_system();
+}
+
 void magic_for(int32_t d, uint64_t* magic, uint32_t* shift) {
     uint32_t L = 0;
     while ((1ull << L) < uint64_t(d)) ++L;
@@ -595,5 +626,11 @@ void launch_coverage(TileTable tiles, int64_t n_tiles, const int32_t* c0, const 
     const size_t smem = size_t(max_tile_ints + 8) * sizeof(int32_t);
     k_coverage<<<unsigned(n_tiles), kThreads, smem, s>>>(tiles, c0, c1, out);
 }
+
+void launch_pack_u8(const int32_t* d_src, int64_t n, uint8_t* d_dst, uint2* ovf, uint32_t cap, uint32_t* d_cnt, cudaStream_t s) {
+    if (n <= 0) return;
+    k_pack_u8<<<unsigned((n + 1023) / 1024), 256, 0, s>>>(d_src, n, d_dst, ovf, cap, d_cnt);
+}
+void launch_publish_reset(uint32_t* d_cnt, uint32_t* host_cnt, cudaStream_t s) { k_publish_reset<<<1, 1, 0, s>>>(d_cnt, host_cnt); }
 
 }  // namespace bsg

@@ -102,6 +102,13 @@ void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, ui
 // the 32 MiB result copies on the device-to-host copy engine.)
 void launch_publish_pair(const int32_t* d_a, const int32_t* d_b, int32_t* dst, cudaStream_t s);
 
+// Result narrowing for the trip over PCIe: dst[i] = min(src[i], 255) for i < n, and every element outside 0..254 also
+// goes, as (i, value), into ovf[0..cap) - which may be pinned host memory - through the counter *cnt (device memory,
+// zero before the launch; it keeps counting past cap, entries beyond cap are dropped).  launch_publish_reset then copies the
+// counter to *host_cnt (pinned host memory) and zeroes it.
+void launch_pack_u8(const int32_t* d_src, int64_t n, uint8_t* d_dst, uint2* ovf, uint32_t cap, uint32_t* d_cnt, cudaStream_t s);
+void launch_publish_reset(uint32_t* d_cnt, uint32_t* host_cnt, cudaStream_t s);
+
 // K3: per tile, binary-search the (tid,pos)-sorted table for the candidate row range (the job of the sort + chunk
 // + sweep in overlapAndPileup, src/bamsignals.cpp:246-285).
 void launch_join(ReadTable t, int64_t n, TileTable tiles, int64_t n_tiles, const DeviceScalars* sc, cudaStream_t s);

@@ -76,7 +76,12 @@ typedef struct bsg_opts {
                                  one device launch */
     int32_t stream_min_ints;  /* result ints that must be final before a portion is counted + shipped while later
                                  batches are still inflating; 0 = default (4 Mi), -1 = never (one pass at the end) */
-    int32_t reserved[7];
+    int32_t result_pack;      /* how a large result crosses PCIe: 0 (default) = one byte per element plus a list of
+                                 (index, value) pairs for the elements above 254, widened to int32 by the host while it
+                                 scatters them into the caller's buffers (a portion with too many such elements travels
+                                 as int32); -1 = always int32; N > 0 = as 0 with room for one pair per N elements
+                                 (default 64) */
+    int32_t reserved[6];
 } bsg_opts;
 
 /* Counters and timings of the last call on this thread (milliseconds; kernel times from CUDA events on the

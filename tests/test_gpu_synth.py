@@ -297,3 +297,22 @@ def test_default_options_mid_scale(gen_dir, preset, gs):
     assert np.array_equal(WL.as_flat(getattr(B, fn)(bam, gr, opts=B.default_opts(batch_bytes=batch), **kw)), want)
     assert B.timings()["n_batches"] >= 3
     assert np.array_equal(WL.as_flat(getattr(B, fn)(bam, gr, **kw)), want)
+
+
+@pytest.mark.parametrize("density,result_pack,what", [(1.0, 0, "list"), (6.0, 0, "list+fallback"), (6.0, 2, "list"), (6.0, 1 << 20, "fallback"),
+                                                      (6.0, -1, "int32")])
+def test_result_narrowing_is_exact(gen_dir, density, result_pack, what):
+    """opts.result_pack: a large result crosses PCIe as bytes + (index, value) pairs for the elements above 254; portions
+    with more such elements than the list holds travel as int32.  Deep coverage (density 6: hundreds of reads per base)
+    puts most elements above 254; every variant must return the oracle's integers."""
+    bam, _ = WL.make_bam("c3", 0.004, gen_dir, density=density)
+    gr, kw, fn = WL.regions("c3", 0.004)
+    want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    if density > 1:
+        assert int((want > 254).sum()) > 70000 and int((want <= 254).sum()) > 1000      # > 1/64 of the 4 M elements
+    got = getattr(B, fn)(bam, gr, opts=B.default_opts(result_pack=result_pack, stream_min_ints=1 << 16), **kw)
+    assert np.array_equal(WL.as_flat(got), want), what
+    # per-region destinations (the R list layout) take the same path
+    got2 = B.bamProfile(bam, gr, binsize=1, ss=True, opts=B.default_opts(result_pack=result_pack))
+    want2 = O.bamProfile(bam, gr, binsize=1, ss=True)
+    same(got2.as_list(), want2.as_list())

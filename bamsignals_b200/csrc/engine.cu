@@ -25,6 +25,7 @@
 #include "bamio.h"
 #include "common.h"
 #include "kernels.cuh"
+#include "hostsimd.h"
 #include "plan.h"
 #include "pool.h"
 
@@ -789,6 +790,7 @@ private:
             if (!c.g_pack_cnt.p) { c.g_pack_cnt.ensure(64); BSG_CUDA(cudaMemset(c.g_pack_cnt.p, 0, 64)); }
         }
         os_stop_ = false; os_abort_ = false;
+        os_wait_ms_ = os_scatter_ms_ = 0;
         os_jobs_.clear();
         os_err_ = Error{0, ""};
         os_thread_ = std::thread([this] { streamer_main(); });
@@ -855,8 +857,11 @@ private:
                 if (k + kOutSlots - 1 < np) e = issue(k + kOutSlots - 1);      // its slot was scattered in iteration k-1
                 if (e != cudaSuccess) break;
                 const int slot = k % kOutSlots;
+                const double tw0 = now_ms();
                 e = cudaEventSynchronize(c.ev_d2h[slot]);
                 if (e != cudaSuccess) break;
+                const double tw1 = now_ms();
+                os_wait_ms_ += tw1 - tw0;
                 const int64_t t_lo = cut[k], base = tile_dev_off_[t_lo], n = cut[k + 1] - t_lo;
                 uint32_t n_ovf = 0;
                 bool packed = ovf_cap[size_t(k)] != 0;
@@ -883,9 +888,7 @@ private:
                         for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
                             int32_t* dst = dst_of(t);
                             if (!dst) continue;
-                            const uint8_t* sp = src + (tile_dev_off_[t] - base);
-                            const int64_t m = ht_.ints[t];
-                            for (int64_t i = 0; i < m; ++i) dst[i] = int32_t(sp[i]);
+                            widen_u8_to_i32(dst, src + (tile_dev_off_[t] - base), ht_.ints[t]);
                         }
                     });
                     const uint2* ov = c.h_ovf[slot].as<uint2>();
@@ -900,10 +903,11 @@ private:
                     pool_->parallel_for(n, grain, [&](int64_t a, int64_t b, int) {
                         for (int64_t t = t_lo + a; t < t_lo + b; ++t) {
                             int32_t* dst = dst_of(t);
-                            if (dst) memcpy(dst, src + (tile_dev_off_[t] - base), size_t(ht_.ints[t]) * 4);
+                            if (dst) copy_i32_stream(dst, src + (tile_dev_off_[t] - base), ht_.ints[t]);
                         }
                     });
                 }
+                os_scatter_ms_ += now_ms() - tw1;
             }
             if (e != cudaSuccess) {
                 std::lock_guard<std::mutex> g(os_m_);
@@ -920,6 +924,7 @@ private:
         }
         os_cv_.notify_all();
         os_thread_.join();
+        if (getenv("BSG_DEBUG")) fprintf(stderr, "[bsg] result streamer: %.1f ms waiting for copies, %.1f ms scattering\n", os_wait_ms_, os_scatter_ms_);
         if (!abort && os_err_.code) throw os_err_;
     }
 
@@ -1381,6 +1386,10 @@ private:
                               c.scalars.as<DeviceScalars>(), c.s_hi);
                 BSG_CUDA(cudaEventRecord(sp.b, c.s_hi));
                 kt_.decode.push_back(sp); kt_.launches += n > 0;
+                // K1 (and the CRC kernel) were the last readers of the raw buffer: inflate(bi + 2) may have it, without
+                // waiting for the counting kernels queued below
+                if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_crc[slot], 0));
+                BSG_CUDA(cudaEventRecord(c.ev_gfree[rslot], c.s_hi));
                 if (n > 0 && cnt_.active) {
                     // (tid, pos) of the last decoded record = how far the sorted read stream has come: count + ship
                     // every tile it finalises while the next batches inflate
@@ -1392,8 +1401,6 @@ private:
                     BSG_CUDA(cudaEventSynchronize(c.ev_front[0]));
                     advance(n_rows_ + n, uint32_t(f[0]), f[1]);
                 }
-                if (opts_.verify_crc) BSG_CUDA(cudaStreamWaitEvent(c.s_hi, c.ev_crc[slot], 0));
-                BSG_CUDA(cudaEventRecord(c.ev_gfree[rslot], c.s_hi));
             }
             n_rows_ += n;
             nvtxRangePop();
@@ -1498,6 +1505,7 @@ private:
     bool os_stop_ = false;
     std::atomic<bool> os_abort_{false};
     Error os_err_{0, ""};
+    double os_wait_ms_ = 0, os_scatter_ms_ = 0;
     // cached tiles
     bool tiles_valid_ = false;
     Mode tiles_mode_ = MODE_COUNT;

@@ -9,6 +9,7 @@
 #include <climits>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -442,6 +443,27 @@ public:
         });
     }
 
+    // Work of a streaming call that needs neither the plan nor the device pipeline - building and uploading the tiles,
+    // starting the result streamer - runs on a thread of its own next to the planner thread; stage() joins it before the
+    // first batch is decoded (C2: 8-11 ms that used to sit in front of the first upload).
+    void defer_setup(std::function<void()> f) {
+        setup_err_ = Error{0, ""};
+        setup_thread_ = std::thread([this, f] {
+            Nvtx r("bsg:setup (tiles + streamer)");
+            try {
+                BSG_CUDA(cudaSetDevice(ctx_->dev));
+                f();
+            } catch (Error& e) { setup_err_ = e; }
+            catch (std::exception& e) { setup_err_ = Error{BSG_EARG, std::string("internal error: ") + e.what()}; }
+        });
+    }
+    void run_deferred() {
+        if (!setup_thread_.joinable()) return;
+        setup_thread_.join();
+        if (setup_err_.code) throw setup_err_;
+    }
+    cudaStream_t setup_stream() const { return ctx_->s_d2h; }      // idle until the result streamer starts
+
     // Fetch + upload (+ decode unless keep_raw) everything the regions need with halo `ext`.
     void stage(int64_t ext, bool keep_raw) {
         if (ext < 0) fail(BSG_EARG, "negative 'ext' values don't make sense");           // src/bamsignals.cpp:243
@@ -452,11 +474,12 @@ public:
             plan_thread_.join();
             if (plan_err_.code) throw plan_err_;
             if (plan_ext_ != ext) fail(BSG_EARG, "internal error: plan started with another halo");
-            t0 -= plan_ms_;                              // ms_plan reports the plan's own duration, ms_fetch what follows it
+            t0 = now_ms() - plan_ms_;                    // ms_plan reports the plan's own duration, ms_fetch what follows it
         } else {
             segs_.clear();
             plan_fetch(bam_, rg_, ext, kSegCBytes, *pool_, &segs_);
         }
+        if (prefault_out_) { prefault_output(prefault_out_, prefault_total_); prefault_out_ = nullptr; }
         // 1 = device inflate, -1 = host zlib pool, 0 = default: device inflate unless the job is tiny.  A device-inflate
         // launch lasts as long as ONE BGZF block takes a single lane (a few ms) however few blocks there are, and a file
         // with a handful of index entry points leaves the device record walk a few long serial chains (the reference's
@@ -523,9 +546,11 @@ public:
         BSG_CUDA(cudaMemsetAsync(c.scalars.p, 0, sizeof(DeviceScalars), c.s_comp));
         if (gpu) {
             run_pipeline_gpu(max_batch, max_offs);
+            run_deferred();                              // (a job without batches)
             tm_.ms_fetch = now_ms() - t0 - tm_.ms_plan;
             return;
         }
+        run_deferred();
         for (int s = 0; s < kSlots && s < int(batches_.size()); ++s) {
             c.h_raw[s].ensure(max_batch + 64);
             c.h_offs[s].ensure((max_offs + max_segs + 8) * sizeof(uint32_t));
@@ -565,7 +590,9 @@ public:
     // while the GPU is busy inflating (the workers are mostly idle in that phase).
     // Started before planning (measured: starting it after the plan makes it compete with the first batch's upload,
     // which is on the critical path; C2 272 -> 289 ms).
-    void request_prefault(int32_t* out, int64_t total) { prefault_output(out, total); }
+    // (the pre-faulting starts when the plan is done: page faults and the planner's allocations fight over the process's
+    // mmap lock - plan 7 -> 15-23 ms when both ran together)
+    void request_prefault(int32_t* out, int64_t total) { prefault_out_ = out; prefault_total_ = total; }
     void prefault_output(int32_t* out, int64_t total) {
         if (!out || total < (int64_t(1) << 22)) return;
         // One atomic `or 0` per page: a write fault that leaves the contents alone, so it may run concurrently with
@@ -592,6 +619,7 @@ public:
     }
     ~Session() {
         if (plan_thread_.joinable()) plan_thread_.join();
+        if (setup_thread_.joinable()) setup_thread_.join();
         stop_streamer(true);
         wait_prefault();
         if (raw_all_.p || offs_all_.p || batch_table_.p) {
@@ -603,15 +631,10 @@ public:
 
     // Tiles depend only on the regions and on (mode, binsize, ss, layout): build + upload them before any device
     // work of the call is queued, and keep them for the next call of a staged session.
-    void prepare_tiles(Mode mode, int32_t binsize, int ss, const int64_t* out_offsets) {
-        Nvtx r("bsg:tiles");
-        DeviceCtx& c = *ctx_;
+    // the layout must be the one allocateList gives (src/bamsignals.cpp:139-192): the host scatter trusts it
+    void validate_layout(Mode mode, int32_t binsize, int ss, const int64_t* out_offsets) const {
         const int64_t R = rg_.R;
         if (!out_offsets) fail(BSG_EARG, "out_offsets is required");
-        if (tiles_valid_ && my_tiles_gen_ == c.tiles_gen && tiles_mode_ == mode && tiles_binsize_ == binsize && tiles_ss_ == ss &&
-            tiles_offsets_.size() == size_t(R + 1) && memcmp(tiles_offsets_.data(), out_offsets, size_t(R + 1) * 8) == 0)
-            return;
-        // the layout must be the one allocateList gives (src/bamsignals.cpp:139-192): the host scatter trusts it
         {
             const int64_t mult = ss ? 2 : 1;
             if (R > 0 && out_offsets[0] < 0) fail(BSG_EARG, "out_offsets must not be negative");
@@ -625,6 +648,18 @@ public:
                                    " (see bsg_output_layout)");
             }
         }
+    }
+    // up: the stream the tile table is uploaded on (and waited for); not the compute stream once inflates are queued on it
+    void prepare_tiles(Mode mode, int32_t binsize, int ss, const int64_t* out_offsets, cudaStream_t up = nullptr) {
+        Nvtx r("bsg:tiles");
+        DeviceCtx& c = *ctx_;
+        const int64_t R = rg_.R;
+        if (!up) up = c.s_comp;
+        if (!out_offsets) fail(BSG_EARG, "out_offsets is required");
+        if (tiles_valid_ && my_tiles_gen_ == c.tiles_gen && tiles_mode_ == mode && tiles_binsize_ == binsize && tiles_ss_ == ss &&
+            tiles_offsets_.size() == size_t(R + 1) && memcmp(tiles_offsets_.data(), out_offsets, size_t(R + 1) * 8) == 0)
+            return;
+        validate_layout(mode, binsize, ss, out_offsets);
         HostTiles& ht = ht_;
         ht = HostTiles();
         // Tile size: as large as shared memory allows (fewer halo re-reads), but small enough that the launch has
@@ -648,9 +683,9 @@ public:
             memcpy(h, ht.rid.data(), nt * 4); memcpy(h + nt * 4, ht.loc.data(), nt * 4);
             memcpy(h + nt * 8, ht.len.data(), nt * 4); memcpy(h + nt * 12, ht.strand.data(), nt * 4);
             memcpy(h + nt * 16, tile_dev_off_.data(), nt * 8);
-            BSG_CUDA(cudaMemcpyAsync(ti, h, nt * 16, cudaMemcpyHostToDevice, c.s_comp));
-            BSG_CUDA(cudaMemcpyAsync(tl, h + nt * 16, nt * 8, cudaMemcpyHostToDevice, c.s_comp));
-            BSG_CUDA(cudaStreamSynchronize(c.s_comp));   // h_tiles is reused by the next call
+            BSG_CUDA(cudaMemcpyAsync(ti, h, nt * 16, cudaMemcpyHostToDevice, up));
+            BSG_CUDA(cudaMemcpyAsync(tl, h + nt * 16, nt * 8, cudaMemcpyHostToDevice, up));
+            BSG_CUDA(cudaStreamSynchronize(up));         // h_tiles is reused by the next call; the kernels that read the tiles are launched after this
         }
         my_tiles_gen_ = ++c.tiles_gen;
         n_tiles_ = nt;
@@ -665,11 +700,11 @@ public:
     // (src/bamsignals.cpp:278); the same observation lets the result leave the device while later batches are still
     // being inflated: a tile is final once the last decoded record's (tid, pos) is >= (rid, end + ext).
     void begin_count(Mode mode, const FilterParams& fp, int32_t binsize, int ss, int64_t ext, int32_t* out,
-                     const int64_t* out_offsets, int32_t* const* out_ptrs, bool want_output) {
+                     const int64_t* out_offsets, int32_t* const* out_ptrs, bool want_output, cudaStream_t tiles_stream = nullptr) {
         DeviceCtx& c = *ctx_;
         const int64_t R = rg_.R;
         stop_streamer(true);                         // left over from a call that failed half-way (staged sessions persist)
-        prepare_tiles(mode, binsize, ss, out_offsets);
+        prepare_tiles(mode, binsize, ss, out_offsets, tiles_stream);
         cnt_ = CountState();
         cnt_.active = true; cnt_.mode = mode; cnt_.fp = fp; cnt_.binsize = binsize; cnt_.ss = ss;
         cnt_.out = out; cnt_.out_offsets = out_offsets; cnt_.out_ptrs = out_ptrs;
@@ -1407,16 +1442,27 @@ private:
         };
 
         const double t_pipe0 = now_ms();
-        if (nb > 0) upload(0);
-        if (nb > 1) upload(1);
-        if (nb > 0) compute(0);
-        for (size_t bi = 0; bi < nb; ++bi) {
-            if (bi + 1 < nb) compute(bi + 1);
-            if (bi + 2 < nb) upload(bi + 2);
-            const double tt = now_ms();
-            finish(bi);
-            t_finish += now_ms() - tt;
-            if (dbg_tl) fprintf(stderr, "[bsg]   host: finish(%zu) entered %.2f, returned %.2f ms after the pipeline started\n", bi, tt - t_pipe0, now_ms() - t_pipe0);
+        size_t n_up = 0, n_comp = 0;
+        auto upload_to = [&](size_t k) { for (; n_up < std::min(k + 1, nb); ++n_up) upload(n_up); };
+        auto compute_to = [&](size_t k) { for (; n_comp < std::min(k + 1, nb); ++n_comp) compute(n_comp); };
+        try {
+            // two batches queued on the device, a third on its way: then the setup the call deferred (tiles, streamer),
+            // on this thread, while the first batch uploads and inflates
+            upload_to(1); compute_to(0); compute_to(1); upload_to(2);
+            run_deferred();
+            for (size_t bi = 0; bi < nb; ++bi) {
+                compute_to(bi + 1);
+                upload_to(bi + 2);
+                const double tt = now_ms();
+                finish(bi);
+                t_finish += now_ms() - tt;
+                if (dbg_tl) fprintf(stderr, "[bsg]   host: finish(%zu) entered %.2f, returned %.2f ms after the pipeline started\n", bi, tt - t_pipe0, now_ms() - t_pipe0);
+            }
+        } catch (...) {
+            // queued copies and kernels still reference this call's buffers
+            cudaStreamSynchronize(c.s_copy); cudaStreamSynchronize(c.s_comp); cudaStreamSynchronize(c.s_walk);
+            cudaStreamSynchronize(c.s_aux); cudaStreamSynchronize(c.s_hi);
+            throw;
         }
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_walk));
@@ -1469,6 +1515,10 @@ private:
 
     struct ResidentBatch { uint64_t raw_base; int64_t offs_base; int64_t n; };
 
+    std::thread setup_thread_;
+    Error setup_err_{0, ""};
+    int32_t* prefault_out_ = nullptr;
+    int64_t prefault_total_ = 0;
     std::shared_ptr<BamFile> bamp_;
     const BamFile& bam_;
     bsg_opts opts_;
@@ -1701,12 +1751,13 @@ int bsg_pileup(const char* bampath, int64_t R, const char* const* seq_levels, in
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         const double t1 = now_ms();
         const int64_t ext = ext_pileup(tlen_filter, shift, pe_mid);
+        const Mode mode = binsize <= 0 ? MODE_COUNT : MODE_PROFILE;
         s.start_plan(ext);
-        s.prepare_tiles(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, binsize, ss != 0, out_offsets);
+        s.validate_layout(mode, binsize, ss != 0, out_offsets);
         const double t2 = now_ms();
-        if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
         const FilterParams fp = make_params(tlen_filter, mapqual, shift, requiredF, filteredF, pe_mid, 0);
-        s.begin_count(binsize <= 0 ? MODE_COUNT : MODE_PROFILE, fp, binsize, ss != 0, ext, out, out_offsets, out_ptrs, true);
+        if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
+        s.defer_setup([&] { s.begin_count(mode, fp, binsize, ss != 0, ext, out, out_offsets, out_ptrs, true, s.setup_stream()); });
         const double t3 = now_ms();
         s.stage(ext, false);
         const double t4 = now_ms();
@@ -1736,10 +1787,10 @@ int bsg_coverage(const char* bampath, int64_t R, const char* const* seq_levels, 
         Session s(bampath, R, seq_levels, n_levels, seq_idx, loc, width, strand, opts);
         const int64_t ext = ext_coverage(tlen_filter, tspan);
         s.start_plan(ext);
-        s.prepare_tiles(MODE_COVERAGE, 1, 0, out_offsets);
-        if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
+        s.validate_layout(MODE_COVERAGE, 1, 0, out_offsets);
         const FilterParams fp = make_params(tlen_filter, mapqual, 0, requiredF, filteredF, 0, tspan);
-        s.begin_count(MODE_COVERAGE, fp, 1, 0, ext, out, out_offsets, out_ptrs, true);
+        if (out && out_offsets) s.request_prefault(out, out_offsets[R]);
+        s.defer_setup([&] { s.begin_count(MODE_COVERAGE, fp, 1, 0, ext, out, out_offsets, out_ptrs, true, s.setup_stream()); });
         s.stage(ext, false);
         s.finish_count();
         s.finish_timings(t0);

@@ -8,9 +8,10 @@
 //   output positions; all literals of a queue in one store; independent short matches replayed concurrently, one lane
 //   each).  The two halves overlap through double-buffered queues and ONE CTA barrier per round.
 // k_crc32: one warp per block: 32 slicing-by-4 pieces folded with carry-less multiplies.
-// k_walk<>: one thread per index entry point (BAI linear-index offsets and chunk bounds are record-aligned); each
-//   walks block_size -> next record until the next entry point; a scan of the counts in between gives every walker
-//   its slice of the offsets array (count pass, scan, write pass; no atomics, deterministic order).
+// k_walk_*: record boundaries between index entry points (BAI linear-index offsets and chunk bounds are record-aligned),
+//   block-parallel: every BGZF block is walked speculatively from its first byte, one thread per entry-point span links
+//   the true chain through the blocks, a scan of the per-span counts gives every span its slice of the offsets array, a
+//   last pass writes the offsets (no atomics, deterministic order).
 //
 // Designs measured and dropped (C2, B200): round 1: per-symbol warp round trip (150 ms), D = 4/8/16
 // lock-step streams per warp with group copies (142-282 ms), one stream per lane doing its own copies (235 ms), one warp
@@ -467,27 +468,170 @@ __device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* raw, uint32_t off)
     return __funnelshift_r(lo, hi, sh);
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(128) k_walk(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
-                                              uint32_t* __restrict__ counts, const uint32_t* __restrict__ base,
-                                              uint32_t* __restrict__ offs, DeviceScalars* sc) {
+// The walk, block-parallel.  A walker is the span between two index entry points; its record chain is serial, and on deep
+// data a span holds tens of thousands of records (C4: 10.8 ms per batch for the longest chains, 2 of 32 lanes busy, the
+// bottleneck of the whole call).  BAM writers start nearly every BGZF block on a record boundary, so:
+//   k_walk_spec   one thread per BLOCK walks from the block's first byte to its end: record count + where the chain lands.
+//                 Pure speculation: nothing it reads is trusted yet.
+//   k_walk_link   one thread per WALKER follows its true chain block by block: where the chain enters a block exactly at
+//                 the block's first byte (and the block lies inside the span), the speculative result IS the chain and the
+//                 block costs one step; otherwise (span borders inside a block, a record straddling into the block) the
+//                 block is walked from the true entry.  Counts per walker + (entry, records before) per block.
+//   k_scan_counts bases of the walkers in the offsets array.
+//   k_walk_write  one thread per block inside a span writes its record offsets from the known entry; one thread per
+//                 walker writes the (at most two) partial blocks at the span's borders.
+// Every chain any thread walks is now at most one block long (~1200 records) plus one step per block of its span.
+struct WalkScratch {       // per batch, n_blocks / n_walkers entries each
+    uint32_t* spec_cnt;    // records on the speculative chain of the block; kSpecBad = it ran into an implausible record
+    uint32_t* spec_end;    // where that chain first reaches or passes the block's end
+    uint32_t* entry;       // block inside a span: where the true chain enters it; kNoOwner = not written by k_walk_write<BLOCK>
+    uint32_t* first;       // ... and how many records of its walker come before it
+    uint32_t* owner;       // ... and the walker
+    uint32_t* last_entry;  // walker: entry + records before of its last, partial block (kNoOwner = none)
+    uint32_t* last_first;
+};
+constexpr uint32_t kSpecBad = 0xffffffffu, kNoOwner = 0xffffffffu;
+
+// one record step: false = the bytes at p are not a plausible record inside [.., lim)
+// A chain only moves forward, one dependent load per record, ~50 bytes further on every time - and caches fill by 32-byte
+// SECTOR, so unassisted every step is a trip to DRAM of its own (the bytes were inflated a moment ago, a batch is several
+// times the L2): measured 0.7 us per record, a 64 KiB block 0.85 ms.  (prefetch.global hints on the next LINES changed
+// nothing: they fetch one sector of the line, not the one the next record starts in.)  Whenever the chain enters a new
+// kilobyte it asks L2 for the whole kilobyte two ahead with ONE bulk prefetch (no registers, no shared memory).
+__device__ __forceinline__ void walk_prefetch(const uint8_t* raw, uint32_t from, uint32_t to, uint32_t lim) {
+    if ((to >> 10) != (from >> 10)) {
+        const uint32_t a = (to & ~1023u) + 2048u;
+        if (a + 16u <= lim) {
+            const uint32_t n = min(1024u, lim - a) & ~15u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(raw + a), "r"(n) : "memory");
+        }
+    }
+}
+// the first three kilobytes of a chain that starts at p
+__device__ __forceinline__ void walk_prefetch_start(const uint8_t* raw, uint32_t p, uint32_t lim) {
+    const uint32_t a = p & ~15u;
+    if (a + 16u <= lim) {
+        const uint32_t n = min(3072u + (p & 1023u), lim - a) & ~15u;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(raw + a), "r"(n) : "memory");
+    }
+}
+__device__ __forceinline__ bool walk_step(const uint8_t* raw, uint32_t& p, uint32_t lim) {
+    if (p + 4 > lim) return false;
+    const uint32_t bs = ld_u32_any(raw, p);
+    if (bs < 32u || bs > 0x7fffffffu || uint64_t(p) + 4 + bs > lim) return false;
+    walk_prefetch(raw, p, p + 4 + bs, lim);
+    p += 4 + bs;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_walk_spec(const uint8_t* __restrict__ raw, const InflateBlock* __restrict__ blocks, int n_blocks,
+                                                   uint32_t raw_end, WalkScratch ws) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
+    uint32_t p = s0, n = 0;
+    bool ok = true;
+    walk_prefetch_start(raw, p, raw_end);
+    while (p < e0) {
+        if (!walk_step(raw, p, raw_end)) { ok = false; break; }
+        ++n;
+    }
+    ws.spec_cnt[b] = ok ? n : kSpecBad;
+    ws.spec_end[b] = p;
+    ws.owner[b] = kNoOwner;
+}
+
+__global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
+                                                   const InflateBlock* __restrict__ blocks, int n_blocks, uint32_t* __restrict__ counts,
+                                                   WalkScratch ws, DeviceScalars* sc) {
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= n_walkers) return;
-    const uint2 wk = walkers[w];
-    uint32_t p = wk.x, n = 0;
-    const uint32_t e = wk.y;
-    uint32_t* o = WRITE ? offs + base[w] : nullptr;
-    bool bad = false;
-    while (p < e) {
-        if (p + 4 > e) { bad = true; break; }
-        const uint32_t bs = ld_u32_any(raw, p);
-        if (bs < 32u || bs > 0x7fffffffu || uint64_t(p) + 4 + bs > e) { bad = true; break; }
-        if (WRITE) o[n] = p;
-        ++n;
-        p += 4 + bs;
+    const uint32_t wb = walkers[w].x, we = walkers[w].y;
+    // the block that holds wb: the last one that starts at or before it
+    int lo = 0, hi = n_blocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].out_off <= wb) lo = mid; else hi = mid - 1;
     }
-    if (!WRITE) counts[w] = n;
+    int b = lo;
+    uint32_t p = wb, n = 0;
+    bool bad = false;
+    ws.last_entry[w] = kNoOwner;
+    walk_prefetch_start(raw, p, we);
+    while (p < we && !bad) {
+        while (b + 1 < n_blocks && blocks[b + 1].out_off <= p) ++b;
+        const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
+        if (p >= e0) {                          // padding between two segments of the batch: no span crosses it
+            bad = true;
+            break;
+        }
+        if (s0 >= wb && e0 <= we) {             // the block lies inside the span: k_walk_write<BLOCK> fills it in
+            ws.entry[b] = p; ws.first[b] = n; ws.owner[b] = uint32_t(w);
+            if (p == s0 && ws.spec_cnt[b] != kSpecBad) {
+                n += ws.spec_cnt[b];
+                p = ws.spec_end[b];
+                continue;
+            }
+        } else if (p != wb) {                   // the span ends inside this block (its first block is walked from wb again)
+            ws.last_entry[w] = p; ws.last_first[w] = n;
+        }
+        const uint32_t stop = min(e0, we);
+        while (p < stop) {
+            if (!walk_step(raw, p, we)) { bad = true; break; }
+            ++n;
+        }
+    }
+    if (p != we) bad = true;                    // the chain must land exactly on the next entry point
+    counts[w] = n;
     if (bad) atomicOr(&sc->status, STATUS_CORRUPT);
+}
+
+// BLOCK: one thread per block inside a span; !BLOCK: one thread per walker, its partial first / last block
+template <bool BLOCK>
+__global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
+                                                    const InflateBlock* __restrict__ blocks, int n_blocks, const uint32_t* __restrict__ base,
+                                                    WalkScratch ws, uint32_t* __restrict__ offs) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (BLOCK) {
+        if (i >= n_blocks || ws.owner[i] == kNoOwner) return;
+        const uint32_t w = ws.owner[i], e0 = blocks[i].out_off + blocks[i].out_len, lim = walkers[w].y;
+        uint32_t p = ws.entry[i];
+        uint32_t* o = offs + base[w] + ws.first[i];
+        walk_prefetch_start(raw, p, lim);
+        while (p < e0) {
+            *o++ = p;
+            if (!walk_step(raw, p, lim)) break;         // (validated by k_walk_link; never taken)
+        }
+    } else {
+        if (i >= n_walkers) return;
+        const uint32_t wb = walkers[i].x, we = walkers[i].y;
+        if (wb >= we) return;
+        int lo = 0, hi = n_blocks - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (blocks[mid].out_off <= wb) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t s0 = blocks[lo].out_off, e0 = s0 + blocks[lo].out_len;
+        if (!(s0 >= wb && e0 <= we)) {                  // the first block is a partial one: [wb, min(e0, we))
+            uint32_t p = wb;
+            uint32_t* o = offs + base[i];
+            const uint32_t stop = min(e0, we);
+            walk_prefetch_start(raw, p, we);
+            while (p < stop) {
+                *o++ = p;
+                if (!walk_step(raw, p, we)) break;
+            }
+        }
+        if (ws.last_entry[i] != kNoOwner) {             // the last block, entered by the chain at last_entry
+            uint32_t p = ws.last_entry[i];
+            uint32_t* o = offs + base[i] + ws.last_first[i];
+            walk_prefetch_start(raw, p, we);
+            while (p < we) {
+                *o++ = p;
+                if (!walk_step(raw, p, we)) break;
+            }
+        }
+    }
 }
 
 // exclusive scan of counts[0..n) into base[0..n), total into *total and (when offs != null) the end sentinel.
@@ -567,16 +711,23 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
     k_crc32<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
 }
 
-void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t* d_counts, uint32_t* d_base,
-                 uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos, DeviceScalars* sc, cudaStream_t s) {
-    if (n_walkers <= 0) {
+void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, const InflateBlock* d_blocks, int n_blocks, uint32_t raw_end,
+                 uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos,
+                 DeviceScalars* sc, cudaStream_t s) {
+    if (n_walkers <= 0 || n_blocks <= 0) {
         k_scan_counts<<<1, 32, 0, s>>>(d_counts, 0, d_base, d_total, d_offs, end_pos);
         return;
     }
-    const int grid = (n_walkers + 127) / 128;
-    k_walk<false><<<grid, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_counts, nullptr, nullptr, sc);
+    WalkScratch ws;
+    ws.spec_cnt = d_scratch; ws.spec_end = ws.spec_cnt + n_blocks; ws.entry = ws.spec_end + n_blocks; ws.first = ws.entry + n_blocks;
+    ws.owner = ws.first + n_blocks; ws.last_entry = ws.owner + n_blocks; ws.last_first = ws.last_entry + n_walkers;
+    const int gb = (n_blocks + 127) / 128, gw = (n_walkers + 127) / 128;
+    k_walk_spec<<<gb, 128, 0, s>>>(d_raw, d_blocks, n_blocks, raw_end, ws);
+    k_walk_link<<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_counts, ws, sc);
     k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
-    k_walk<true><<<grid, 128, 0, s>>>(d_raw, d_walkers, n_walkers, nullptr, d_base, d_offs, sc);
+    k_walk_write<true><<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
+    k_walk_write<false><<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
 }
+size_t walk_scratch_words(int n_blocks, int n_walkers) { return size_t(n_blocks) * 5 + size_t(n_walkers) * 2 + 16; }
 
 }  // namespace bsg

@@ -471,28 +471,33 @@ __device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* raw, uint32_t off)
 // The walk, block-parallel.  A walker is the span between two index entry points; its record chain is serial, and on deep
 // data a span holds tens of thousands of records (C4: 10.8 ms per batch for the longest chains, 2 of 32 lanes busy, the
 // bottleneck of the whole call).  BAM writers start nearly every BGZF block on a record boundary, so:
-//   k_walk_spec   one thread per BLOCK walks from the block's first byte to its end: record count + where the chain lands.
-//                 Pure speculation: nothing it reads is trusted yet.
-//   k_walk_link   one thread per WALKER follows its true chain block by block: where the chain enters a block exactly at
-//                 the block's first byte (and the block lies inside the span), the speculative result IS the chain and the
-//                 block costs one step; otherwise (span borders inside a block, a record straddling into the block) the
-//                 block is walked from the true entry.  Counts per walker + (entry, records before) per block.
+//   k_walk_spec   one thread per BLOCK walks from the block's first byte to its end: record count, where the chain lands,
+//                 and for every entry point inside the block whether the chain passes through it and after how many
+//                 records (its RANK).  Pure speculation - but an entry point IS a record boundary: from an entry point
+//                 that lies on the block's chain onwards, that chain is the true one.
+//   k_walk_link   one thread per WALKER counts its records block by block in O(1) steps per block: first block
+//                 = (block's count - rank of its begin), blocks inside the span = their count if the chain enters them at
+//                 their first byte, last block = rank of its end.  Where speculation does not apply (a record straddling
+//                 into a block, an entry point off the block's chain) it walks that piece itself.
 //   k_scan_counts bases of the walkers in the offsets array.
-//   k_walk_write  one thread per block inside a span writes its record offsets from the known entry; one thread per
-//                 walker writes the (at most two) partial blocks at the span's borders.
-// Every chain any thread walks is now at most one block long (~1200 records) plus one step per block of its span.
-struct WalkScratch {       // per batch, n_blocks / n_walkers entries each
-    uint32_t* spec_cnt;    // records on the speculative chain of the block; kSpecBad = it ran into an implausible record
-    uint32_t* spec_end;    // where that chain first reaches or passes the block's end
-    uint32_t* entry;       // block inside a span: where the true chain enters it; kNoOwner = not written by k_walk_write<BLOCK>
-    uint32_t* first;       // ... and how many records of its walker come before it
-    uint32_t* owner;       // ... and the walker
-    uint32_t* last_entry;  // walker: entry + records before of its last, partial block (kNoOwner = none)
+//   k_walk_write  one thread per block writes the offsets of its chain: records from an on-chain entry point j onwards go to
+//                 base[j] + (rank - rank of j), those before the first entry point continue the walker in front if the chain
+//                 truly entered the block at its first byte; one thread per walker writes the pieces it had to walk itself.
+// Every chain any thread walks is at most one block long (~1200 records).
+struct WalkScratch {       // per batch; n_blocks / n_walkers entries each
+    uint32_t* spec_cnt;    // block: records on its speculative chain; kSpecBad = the chain ran into an implausible record
+    uint32_t* spec_end;    // block: where that chain first reaches or passes the block's end
+    uint32_t* entry;       // block inside a span: where the true chain enters it; with owner / first set by k_walk_link
+    uint32_t* first;       // ... how many records of its walker come before it
+    uint32_t* owner;       // ... and the walker (kNoOwner: not inside one span)
+    uint32_t* entry_true;  // block: 1 = the true chain enters it exactly at its first byte
+    uint32_t* rank;        // walker: rank of its begin on its block's speculative chain (kSpecBad = not on it)
+    uint32_t* self_first;  // walker: 1 = it walked (and writes) its piece of its first block itself
+    uint32_t* last_entry;  // walker: entry + records before of a last, partial block it walked itself (kNoOwner = none)
     uint32_t* last_first;
 };
 constexpr uint32_t kSpecBad = 0xffffffffu, kNoOwner = 0xffffffffu;
 
-// one record step: false = the bytes at p are not a plausible record inside [.., lim)
 // A chain only moves forward, one dependent load per record, ~50 bytes further on every time - and caches fill by 32-byte
 // SECTOR, so unassisted every step is a trip to DRAM of its own (the bytes were inflated a moment ago, a batch is several
 // times the L2): measured 0.7 us per record, a 64 KiB block 0.85 ms.  (prefetch.global hints on the next LINES changed
@@ -524,21 +529,53 @@ __device__ __forceinline__ bool walk_step(const uint8_t* raw, uint32_t& p, uint3
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_walk_spec(const uint8_t* __restrict__ raw, const InflateBlock* __restrict__ blocks, int n_blocks,
-                                                   uint32_t raw_end, WalkScratch ws) {
+// index of the first walker whose begin is >= pos
+__device__ __forceinline__ int first_walker_at_or_after(const uint2* __restrict__ walkers, int n_walkers, uint32_t pos) {
+    int lo = 0, hi = n_walkers;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (walkers[mid].x < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// index of the block that holds pos: the last one that starts at or before it
+__device__ __forceinline__ int block_of(const InflateBlock* __restrict__ blocks, int n_blocks, uint32_t pos) {
+    int lo = 0, hi = n_blocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].out_off <= pos) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k_walk_spec(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
+                                                   const InflateBlock* __restrict__ blocks, int n_blocks, uint32_t raw_end, WalkScratch ws) {
     const int b = blockIdx.x * 128 + threadIdx.x;
     if (b >= n_blocks) return;
     const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
+    int j = first_walker_at_or_after(walkers, n_walkers, s0);         // entry points inside the block: walkers[j..] while < e0
+    uint32_t next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
     uint32_t p = s0, n = 0;
     bool ok = true;
     walk_prefetch_start(raw, p, raw_end);
     while (p < e0) {
+        while (next <= p) {                                           // an entry point reached (rank n) or jumped over
+            ws.rank[j] = next == p ? n : kSpecBad;
+            ++j;
+            next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
+        }
         if (!walk_step(raw, p, raw_end)) { ok = false; break; }
         ++n;
+    }
+    for (; next != 0xffffffffu; ) {                                   // entry points behind a chain that broke off
+        ws.rank[j] = kSpecBad;
+        ++j;
+        next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
     }
     ws.spec_cnt[b] = ok ? n : kSpecBad;
     ws.spec_end[b] = p;
     ws.owner[b] = kNoOwner;
+    ws.entry_true[b] = 0u;
 }
 
 __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
@@ -547,35 +584,45 @@ __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ r
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= n_walkers) return;
     const uint32_t wb = walkers[w].x, we = walkers[w].y;
-    // the block that holds wb: the last one that starts at or before it
-    int lo = 0, hi = n_blocks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (blocks[mid].out_off <= wb) lo = mid; else hi = mid - 1;
-    }
-    int b = lo;
+    // is the walker's end an entry point on the speculative chain of its block?  (then rank[w + 1] counts the records of
+    // that block in front of it)
+    const bool end_ranked = w + 1 < n_walkers && walkers[w + 1].x == we && ws.rank[w + 1] != kSpecBad;
+    int b = block_of(blocks, n_blocks, wb);
     uint32_t p = wb, n = 0;
     bool bad = false;
     ws.last_entry[w] = kNoOwner;
-    walk_prefetch_start(raw, p, we);
+    ws.self_first[w] = 0u;
+    if (p < we && p != blocks[b].out_off) {
+        // the span begins inside a block
+        const uint32_t e0 = blocks[b].out_off + blocks[b].out_len;
+        const uint32_t r0 = ws.rank[w];
+        if (r0 != kSpecBad && e0 <= we && ws.spec_cnt[b] != kSpecBad) { n = ws.spec_cnt[b] - r0; p = ws.spec_end[b]; }
+        else if (r0 != kSpecBad && e0 > we && end_ranked) { n = ws.rank[w + 1] - r0; p = we; }
+        else {
+            ws.self_first[w] = 1u;
+            const uint32_t stop = min(e0, we);
+            walk_prefetch_start(raw, p, we);
+            while (p < stop) {
+                if (!walk_step(raw, p, we)) { bad = true; break; }
+                ++n;
+            }
+        }
+    }
     while (p < we && !bad) {
         while (b + 1 < n_blocks && blocks[b + 1].out_off <= p) ++b;
         const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
-        if (p >= e0) {                          // padding between two segments of the batch: no span crosses it
-            bad = true;
-            break;
-        }
-        if (s0 >= wb && e0 <= we) {             // the block lies inside the span: k_walk_write<BLOCK> fills it in
+        if (p >= e0) { bad = true; break; }     // padding between two segments of the batch: no span crosses it
+        if (p == s0) ws.entry_true[b] = 1u;
+        const bool spec_ok = p == s0 && ws.spec_cnt[b] != kSpecBad;
+        if (e0 <= we) {                         // the block lies inside the span
             ws.entry[b] = p; ws.first[b] = n; ws.owner[b] = uint32_t(w);
-            if (p == s0 && ws.spec_cnt[b] != kSpecBad) {
-                n += ws.spec_cnt[b];
-                p = ws.spec_end[b];
-                continue;
-            }
-        } else if (p != wb) {                   // the span ends inside this block (its first block is walked from wb again)
+            if (spec_ok) { n += ws.spec_cnt[b]; p = ws.spec_end[b]; continue; }
+        } else {                                // the span ends inside this block
+            if (spec_ok && end_ranked) { n += ws.rank[w + 1]; p = we; continue; }
             ws.last_entry[w] = p; ws.last_first[w] = n;
         }
         const uint32_t stop = min(e0, we);
+        walk_prefetch_start(raw, p, we);
         while (p < stop) {
             if (!walk_step(raw, p, we)) { bad = true; break; }
             ++n;
@@ -586,36 +633,57 @@ __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ r
     if (bad) atomicOr(&sc->status, STATUS_CORRUPT);
 }
 
-// BLOCK: one thread per block inside a span; !BLOCK: one thread per walker, its partial first / last block
+// BLOCK: one thread per block; !BLOCK: one thread per walker, the pieces it walked itself in k_walk_link
 template <bool BLOCK>
 __global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
                                                     const InflateBlock* __restrict__ blocks, int n_blocks, const uint32_t* __restrict__ base,
                                                     WalkScratch ws, uint32_t* __restrict__ offs) {
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (BLOCK) {
-        if (i >= n_blocks || ws.owner[i] == kNoOwner) return;
-        const uint32_t w = ws.owner[i], e0 = blocks[i].out_off + blocks[i].out_len, lim = walkers[w].y;
-        uint32_t p = ws.entry[i];
-        uint32_t* o = offs + base[w] + ws.first[i];
-        walk_prefetch_start(raw, p, lim);
+        if (i >= n_blocks) return;
+        const uint32_t s0 = blocks[i].out_off, e0 = s0 + blocks[i].out_len;
+        if (ws.owner[i] != kNoOwner) {                  // inside one span: from where the true chain enters it
+            const uint32_t w = ws.owner[i], lim = walkers[w].y;
+            uint32_t p = ws.entry[i];
+            uint32_t* o = offs + base[w] + ws.first[i];
+            walk_prefetch_start(raw, p, lim);
+            while (p < e0) {
+                *o++ = p;
+                if (!walk_step(raw, p, lim)) break;     // (validated by k_walk_link; never taken)
+            }
+            return;
+        }
+        // a block with entry points inside: its speculative chain, attributed walker by walker
+        int j = first_walker_at_or_after(walkers, n_walkers, s0);
+        if (j >= n_walkers || walkers[j].x >= e0) return;
+        uint32_t next = walkers[j].x;
+        // records in front of the first entry point continue the walker before it - if the chain truly entered at s0
+        bool live = ws.entry_true[i] != 0u && ws.rank[j] != kSpecBad && j > 0 && walkers[j - 1].y == next;
+        uint32_t idx0 = live ? base[j] - ws.rank[j] : 0u, lim = next;      // offs index of the chain's record 0; end of the current walker
+        uint32_t p = s0, n = 0;
+        const uint32_t raw_end = blocks[n_blocks - 1].out_off + blocks[n_blocks - 1].out_len;
+        walk_prefetch_start(raw, p, raw_end);
         while (p < e0) {
-            *o++ = p;
-            if (!walk_step(raw, p, lim)) break;         // (validated by k_walk_link; never taken)
+            while (next <= p) {
+                if (next == p && ws.rank[j] == n) { live = true; idx0 = base[j] - n; lim = walkers[j].y; }
+                else live = false;                      // an entry point off the chain: what follows is not verified
+                ++j;
+                next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
+            }
+            if (live && p >= lim) live = false;         // behind the last walker of a segment
+            if (live) offs[idx0 + n] = p;
+            if (!walk_step(raw, p, raw_end)) break;
+            ++n;
         }
     } else {
         if (i >= n_walkers) return;
         const uint32_t wb = walkers[i].x, we = walkers[i].y;
         if (wb >= we) return;
-        int lo = 0, hi = n_blocks - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (blocks[mid].out_off <= wb) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t s0 = blocks[lo].out_off, e0 = s0 + blocks[lo].out_len;
-        if (!(s0 >= wb && e0 <= we)) {                  // the first block is a partial one: [wb, min(e0, we))
+        if (ws.self_first[i]) {                         // [wb, min(end of its block, we))
+            const int b = block_of(blocks, n_blocks, wb);
+            const uint32_t stop = min(blocks[b].out_off + blocks[b].out_len, we);
             uint32_t p = wb;
             uint32_t* o = offs + base[i];
-            const uint32_t stop = min(e0, we);
             walk_prefetch_start(raw, p, we);
             while (p < stop) {
                 *o++ = p;
@@ -720,14 +788,16 @@ void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, co
     }
     WalkScratch ws;
     ws.spec_cnt = d_scratch; ws.spec_end = ws.spec_cnt + n_blocks; ws.entry = ws.spec_end + n_blocks; ws.first = ws.entry + n_blocks;
-    ws.owner = ws.first + n_blocks; ws.last_entry = ws.owner + n_blocks; ws.last_first = ws.last_entry + n_walkers;
+    ws.owner = ws.first + n_blocks; ws.entry_true = ws.owner + n_blocks;
+    ws.rank = ws.entry_true + n_blocks; ws.self_first = ws.rank + n_walkers; ws.last_entry = ws.self_first + n_walkers;
+    ws.last_first = ws.last_entry + n_walkers;
     const int gb = (n_blocks + 127) / 128, gw = (n_walkers + 127) / 128;
-    k_walk_spec<<<gb, 128, 0, s>>>(d_raw, d_blocks, n_blocks, raw_end, ws);
+    k_walk_spec<<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, raw_end, ws);
     k_walk_link<<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_counts, ws, sc);
     k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
     k_walk_write<true><<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
     k_walk_write<false><<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
 }
-size_t walk_scratch_words(int n_blocks, int n_walkers) { return size_t(n_blocks) * 5 + size_t(n_walkers) * 2 + 16; }
+size_t walk_scratch_words(int n_blocks, int n_walkers) { return size_t(n_blocks) * 6 + size_t(n_walkers) * 4 + 16; }
 
 }  // namespace bsg

@@ -233,7 +233,7 @@ class BsgTimings(C.Structure):
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
                 ("ms_decode", C.c_double), ("ms_filter", C.c_double), ("ms_join", C.c_double),
                 ("ms_count", C.c_double), ("ms_inflate_gpu", C.c_double), ("ms_kernels", C.c_double),
-                ("ms_device", C.c_double), ("reserved", C.c_double * 7)]
+                ("ms_device", C.c_double), ("bytes_d2h", C.c_double), ("reserved", C.c_double * 6)]
 
 
 def lib():

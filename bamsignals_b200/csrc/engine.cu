@@ -722,6 +722,7 @@ public:
             run = std::max(run, uint64_t(uint32_t(ht_.rid[t])) << 32 | uint64_t(uint32_t(std::max<int64_t>(e, 0))));
             tile_final_key_[t] = run;
         }
+        os_bytes_ = 0;
         if (cnt_.want_output) start_streamer();
     }
 
@@ -752,6 +753,7 @@ public:
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         hi_prio_ = false;
         tm_.ms_d2h = now_ms() - t_d2h;
+        tm_.bytes_d2h = os_bytes_ + double(sizeof(DeviceScalars));
         cnt_.active = false;
         const DeviceScalars* hs = c.h_scalars.as<DeviceScalars>();
         check_status(hs->status);
@@ -825,7 +827,7 @@ private:
             if (!c.g_pack_cnt.p) { c.g_pack_cnt.ensure(64); BSG_CUDA(cudaMemset(c.g_pack_cnt.p, 0, 64)); }
         }
         os_stop_ = false; os_abort_ = false;
-        os_wait_ms_ = os_scatter_ms_ = 0;
+        os_wait_ms_ = os_scatter_ms_ = 0; os_bytes_ = 0;
         os_jobs_.clear();
         os_err_ = Error{0, ""};
         os_thread_ = std::thread([this] { streamer_main(); });
@@ -881,8 +883,10 @@ private:
                     launch_pack_u8(src, ints, c.g_pack[slot].as<uint8_t>(), c.h_ovf[slot].as<uint2>(), cap, c.g_pack_cnt.as<uint32_t>() + slot, c.s_d2h);
                     launch_publish_reset(c.g_pack_cnt.as<uint32_t>() + slot, c.h_pack_cnt.as<uint32_t>() + slot, c.s_d2h);
                     r = cudaMemcpyAsync(c.h_out[slot].p, c.g_pack[slot].p, size_t(ints), cudaMemcpyDeviceToHost, c.s_d2h);
+                    os_bytes_ += double(ints) + 4;
                 } else {
                     r = cudaMemcpyAsync(c.h_out[slot].p, src, size_t(ints) * 4, cudaMemcpyDeviceToHost, c.s_d2h);
+                    os_bytes_ += double(ints) * 4;
                 }
                 if (r == cudaSuccess) r = cudaEventRecord(c.ev_d2h[slot], c.s_d2h);
                 return r;
@@ -902,7 +906,9 @@ private:
                 bool packed = ovf_cap[size_t(k)] != 0;
                 if (packed) {
                     n_ovf = c.h_pack_cnt.as<uint32_t>()[slot];
+                    os_bytes_ += 8.0 * std::min(n_ovf, ovf_cap[size_t(k)]);
                     if (n_ovf > ovf_cap[size_t(k)]) {
+                        os_bytes_ += double(tile_dev_off_[cut[k + 1]] - base) * 4;
                         // too many large elements for the list: this piece travels again, as int32 (the copies already queued
                         // for the next pieces go first; it is the rare case)
                         e = cudaMemcpyAsync(c.h_out[slot].p, c.out.as<int32_t>() + base, size_t(tile_dev_off_[cut[k + 1]] - base) * 4,
@@ -1556,7 +1562,7 @@ private:
     bool os_stop_ = false;
     std::atomic<bool> os_abort_{false};
     Error os_err_{0, ""};
-    double os_wait_ms_ = 0, os_scatter_ms_ = 0;
+    double os_wait_ms_ = 0, os_scatter_ms_ = 0, os_bytes_ = 0;
     // cached tiles
     bool tiles_valid_ = false;
     Mode tiles_mode_ = MODE_COUNT;
@@ -1683,7 +1689,7 @@ void run_multi_device(const char* bampath, int64_t R, const char* const* seq_lev
         a.ms_decode = std::max(a.ms_decode, t.ms_decode); a.ms_filter = std::max(a.ms_filter, t.ms_filter);
         a.ms_join = std::max(a.ms_join, t.ms_join); a.ms_count = std::max(a.ms_count, t.ms_count);
         a.ms_inflate_gpu = std::max(a.ms_inflate_gpu, t.ms_inflate_gpu); a.ms_kernels = std::max(a.ms_kernels, t.ms_kernels);
-        a.ms_device = std::max(a.ms_device, t.ms_device);
+        a.ms_device = std::max(a.ms_device, t.ms_device); a.bytes_d2h += t.bytes_d2h;
     }
     a.n_devices = nd;
     a.ms_total = now_ms() - t0;

@@ -239,7 +239,7 @@ def measure_ours(args, preset, gs, rank, world, local_rank, dist, barrier, sampl
         h2d = te["bytes_compressed"] + 20 * (te["bytes_inflated"] // 65280 + 1) + 24 * te["n_tiles"]
     else:                   # inflated bytes + record offsets + tiles
         h2d = te["bytes_inflated"] + 4 * (te["records"] + te["n_batches"]) + 24 * te["n_tiles"]
-    out.update(e2e_ms=e2e_ms, per_call=per_call, te=te, h2d=h2d, d2h=4 * te["out_elems"], e_launch=e_launch)
+    out.update(e2e_ms=e2e_ms, per_call=per_call, te=te, h2d=h2d, d2h=te["bytes_d2h"], e_launch=e_launch)
 
     # ---- parity of what was timed: the last timed call's result vs the CPU checker ----------------------------------
     units = float(info["records"])

@@ -102,7 +102,8 @@ typedef struct bsg_timings {
     double ms_total, ms_plan, ms_fetch, ms_h2d, ms_d2h;
     double ms_decode, ms_filter, ms_join, ms_count, ms_inflate_gpu, ms_kernels;
     double ms_device;         /* first to last device event of the call on the compute stream (kernels + gaps) */
-    double reserved[7];
+    double bytes_d2h;         /* result bytes that crossed PCIe device -> host (packed bytes + (index, value) pairs, or int32) */
+    double reserved[6];
 } bsg_timings;
 
 /* bamCount (binsize <= 0) and bamProfile (binsize >= 1).  Argument order follows pileup_core

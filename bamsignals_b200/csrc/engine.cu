@@ -1185,7 +1185,7 @@ private:
         const std::vector<uint64_t>& ent = bam_.entry_points();
         uint64_t raw_base = 0; int64_t offs_base = 0;
         struct Up {             // what compute() and finish() need to know about an uploaded batch
-            int n_blocks = 0, n_walkers = 0; uint32_t end_pos = 0, raw_end = 0;
+            int n_blocks = 0, n_walkers = 0; uint32_t end_pos = 0, raw_end = 0, max_span = 0;
             uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0;
         };
         std::vector<Up> ups(nb);
@@ -1282,6 +1282,8 @@ private:
             }
             up.raw_base = raw_base; up.offs_base = offs_base;
             up.n_blocks = int(blocks.size()); up.n_walkers = int(walkers.size()); up.end_pos = end_pos; up.raw_end = uint32_t(ubase);
+            for (const uint2& wk : walkers) up.max_span = std::max(up.max_span, wk.y - wk.x);
+            if (opts_.walk_scheme == 1) up.max_span = 0; else if (opts_.walk_scheme == 2) up.max_span = 0xffffffffu;
             // ---- compressed bytes -> device ------------------------------------------------------------------------------------
             Span sph{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sph.a, c.s_copy));
@@ -1396,12 +1398,12 @@ private:
             BSG_CUDA(cudaStreamWaitEvent(ws, c.ev_inflated[slot], 0));
             Span spw{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(spw.a, ws));
-            launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, up.raw_end,
+            launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, up.max_span, c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, up.raw_end,
                         c.g_wscr[slot].as<uint32_t>(), c.g_counts[slot].as<uint32_t>(), c.g_base[slot].as<uint32_t>(),
                         c.h_total.as<uint32_t>() + slot, up.d_offs, up.end_pos, c.scalars.as<DeviceScalars>(), ws);
             BSG_CUDA(cudaEventRecord(spw.b, ws));
             walk_spans.push_back(spw);
-            kt_.launches += (up.n_blocks ? 1 : 0) + ((up.n_walkers && up.n_blocks) ? 5 : 1);
+            kt_.launches += (up.n_blocks ? 1 : 0) + ((up.n_walkers && up.n_blocks) ? (up.max_span <= (96u << 10) ? 3 : 5) : 1);
             // (the record count lands in pinned host memory straight from the scan kernel: a 4-byte cudaMemcpy would queue
             // behind the 32 MiB result copies on the device-to-host engine - measured: up to 6 ms per batch)
             BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));

@@ -94,10 +94,11 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
                   cudaStream_t s);
 // Record-boundary walk between index entry points: walkers[w] = (begin, end) byte positions in d_raw, both record
 // boundaries, each inside one run of consecutive blocks (d_blocks[0..n_blocks) in out_off order; raw_end = end of the last
-// one).  Fills d_offs[0..total] (+ end sentinel) and *d_total; d_scratch: walk_scratch_words() uint32 of device memory.
-void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, const InflateBlock* d_blocks, int n_blocks, uint32_t raw_end,
-                 uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos,
-                 DeviceScalars* sc, cudaStream_t s);
+// one); max_span = the longest walker in bytes (short spans take a simpler scheme).  Fills d_offs[0..total] (+ end
+// sentinel) and *d_total; d_scratch: walk_scratch_words() uint32 of device memory.
+void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t max_span, const InflateBlock* d_blocks, int n_blocks,
+                 uint32_t raw_end, uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs,
+                 uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
 size_t walk_scratch_words(int n_blocks, int n_walkers);
 
 // dst[0] = *d_a, dst[1] = *d_b by a one-thread kernel; dst may be pinned host memory.  (Control values of the streaming

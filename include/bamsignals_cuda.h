@@ -81,7 +81,10 @@ typedef struct bsg_opts {
                                  scatters them into the caller's buffers (a portion with too many such elements travels
                                  as int32); -1 = always int32; N > 0 = as 0 with room for one pair per N elements
                                  (default 64) */
-    int32_t reserved[6];
+    int32_t walk_scheme;      /* device record walk between index entry points: 0 (default) = per span when no span of
+                                 the batch exceeds 96 KiB, else block-parallel (speculative chain per BGZF block, spans
+                                 linked through the blocks); 1 / 2 force the one / the other */
+    int32_t reserved[5];
 } bsg_opts;
 
 /* Counters and timings of the last call on this thread (milliseconds; kernel times from CUDA events on the

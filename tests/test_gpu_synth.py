@@ -316,3 +316,18 @@ def test_result_narrowing_is_exact(gen_dir, density, result_pack, what):
     got2 = B.bamProfile(bam, gr, binsize=1, ss=True, opts=B.default_opts(result_pack=result_pack))
     want2 = O.bamProfile(bam, gr, binsize=1, ss=True)
     same(got2.as_list(), want2.as_list())
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+@pytest.mark.parametrize("preset,gs,straddle", [("c4", 0.002, 0.05), ("c5", 0.002, 0.6), ("c2", 0.002, 0.0)])
+def test_walk_schemes_agree(gen_dir, preset, gs, straddle, scheme):
+    """opts.walk_scheme: the per-span record walk and the block-parallel one (speculative chain per BGZF block, spans
+    linked through the blocks) must both find every record - also when most blocks begin inside a record (straddle 0.6:
+    the speculation fails, the true chain is re-walked) and across many small batches."""
+    bam, _ = WL.make_bam(preset, gs, gen_dir, straddle=straddle, unplaced=3)
+    gr, kw, fn = WL.regions(preset, gs)
+    want = WL.as_flat(getattr(O, fn)(bam, gr, nthreads=8, **kw))
+    for batch in (0, 1 << 18):
+        got = getattr(B, fn)(bam, gr, opts=B.default_opts(gpu_inflate=1, walk_scheme=scheme, batch_bytes=batch), **kw)
+        assert np.array_equal(WL.as_flat(got), want), (scheme, batch)
+        assert B.timings()["records"] > 0

@@ -503,6 +503,8 @@ constexpr uint32_t kSpecBad = 0xffffffffu, kNoOwner = 0xffffffffu;
 // times the L2): measured 0.7 us per record, a 64 KiB block 0.85 ms.  (prefetch.global hints on the next LINES changed
 // nothing: they fetch one sector of the line, not the one the next record starts in.)  Whenever the chain enters a new
 // kilobyte it asks L2 for the whole kilobyte two ahead with ONE bulk prefetch (no registers, no shared memory).
+// (tools/probes/chain_probe.cu: a dependent step costs ~500 ns cold, ~420 ns with this or with four per-sector prefetches
+// per line, ~235 ns when everything is L2-resident: the floor of a chain through global memory on this GPU.)
 __device__ __forceinline__ void walk_prefetch(const uint8_t* raw, uint32_t from, uint32_t to, uint32_t lim) {
     if ((to >> 10) != (from >> 10)) {
         const uint32_t a = (to & ~1023u) + 2048u;

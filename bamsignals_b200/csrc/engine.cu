@@ -100,7 +100,7 @@ struct DeviceCtx {
     uint64_t tiles_gen = 0;                     // bumped whenever a Session uploads tiles: a staged Session's cached tiles are
                                                 // only valid while no other call has replaced them on this device
     // GPU inflate: an upload ring of kUp slots (compressed bytes, descriptors, walk scratch) and two raw / offsets buffers
-    DevBuf g_comp[kUp], g_blocks[kUp], g_crc[kUp], g_walkers[kUp], g_counts[kUp], g_base[kUp], g_wscr[kUp], g_raw[2], g_offs[2], g_total;
+    DevBuf g_comp[kUp], g_blocks[kUp], g_crc[kUp], g_walkers[kUp], g_counts[kUp], g_base[kUp], g_wscr[kUp], g_spec[kUp], g_raw[2], g_offs[2], g_total;
     PinBuf h_total, h_desc[kUp];
     cudaEvent_t ev_pin[kSlots] = {}, ev_up[kUp] = {}, ev_total[kUp] = {}, ev_inflated[kUp] = {}, ev_crc[kUp] = {}, ev_gfree[2] = {};
     PinBuf h_scalars, h_out[kOutSlots], h_tiles, h_front, h_ovf[kOutSlots], h_pack_cnt;
@@ -173,7 +173,7 @@ struct DeviceCtx {
         for (int i = 0; i < 2; ++i) { g_raw[i].release(); g_offs[i].release(); cudaEventDestroy(ev_gfree[i]); }
         for (int i = 0; i < kUp; ++i) {
             g_comp[i].release(); g_blocks[i].release(); g_crc[i].release(); g_walkers[i].release();
-            g_counts[i].release(); g_base[i].release(); g_wscr[i].release(); h_desc[i].release();
+            g_counts[i].release(); g_base[i].release(); g_wscr[i].release(); g_spec[i].release(); h_desc[i].release();
             cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_total[i]); cudaEventDestroy(ev_inflated[i]); cudaEventDestroy(ev_crc[i]);
         }
         for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev_pin[i]);
@@ -1185,7 +1185,7 @@ private:
         const std::vector<uint64_t>& ent = bam_.entry_points();
         uint64_t raw_base = 0; int64_t offs_base = 0;
         struct Up {             // what compute() and finish() need to know about an uploaded batch
-            int n_blocks = 0, n_walkers = 0; uint32_t end_pos = 0, raw_end = 0, max_span = 0;
+            int n_blocks = 0, n_walkers = 0; uint32_t end_pos = 0, raw_end = 0; int scheme = 2;
             uint8_t* d_raw = nullptr; uint32_t* d_offs = nullptr; uint64_t raw_base = 0; int64_t offs_base = 0;
         };
         std::vector<Up> ups(nb);
@@ -1269,6 +1269,7 @@ private:
             c.g_counts[slot].ensure(walkers.size() * 4 + 64);
             c.g_base[slot].ensure(walkers.size() * 4 + 64);
             c.g_wscr[slot].ensure(walk_scratch_words(int(blocks.size()), int(walkers.size())) * 4);
+            c.g_spec[slot].ensure(inflate_spec_words(int(blocks.size())) * 4);
             if (keep_raw_) {
                 up.d_raw = raw_all_.as<uint8_t>() + raw_base;
                 up.d_offs = offs_all_.as<uint32_t>() + offs_base;
@@ -1282,8 +1283,11 @@ private:
             }
             up.raw_base = raw_base; up.offs_base = offs_base;
             up.n_blocks = int(blocks.size()); up.n_walkers = int(walkers.size()); up.end_pos = end_pos; up.raw_end = uint32_t(ubase);
-            for (const uint2& wk : walkers) up.max_span = std::max(up.max_span, wk.y - wk.x);
-            if (opts_.walk_scheme == 1) up.max_span = 0; else if (opts_.walk_scheme == 2) up.max_span = 0xffffffffu;
+            {   // spans of less than a block and a half are cheapest followed one by one (C2: 16 kb index windows, ~500 records)
+                uint32_t max_span = 0;
+                for (const uint2& wk : walkers) max_span = std::max(max_span, wk.y - wk.x);
+                up.scheme = opts_.walk_scheme == 1 ? 1 : (opts_.walk_scheme == 2 ? 2 : (max_span <= (96u << 10) ? 1 : 2));
+            }
             // ---- compressed bytes -> device ------------------------------------------------------------------------------------
             Span sph{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sph.a, c.s_copy));
@@ -1373,7 +1377,7 @@ private:
             Span sp{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(sp.a, c.s_comp));
             launch_inflate(c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, c.g_comp[slot].as<uint8_t>(), up.d_raw,
-                           c.scalars.as<DeviceScalars>(), c.s_comp);
+                           up.scheme == 1 ? nullptr : c.g_spec[slot].as<uint32_t>(), c.scalars.as<DeviceScalars>(), c.s_comp);
             BSG_CUDA(cudaEventRecord(c.ev_inflated[slot], c.s_comp));
             BSG_CUDA(cudaEventRecord(sp.b, c.s_comp));
             inflate_spans.push_back(sp);
@@ -1398,12 +1402,13 @@ private:
             BSG_CUDA(cudaStreamWaitEvent(ws, c.ev_inflated[slot], 0));
             Span spw{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(spw.a, ws));
-            launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, up.max_span, c.g_blocks[slot].as<InflateBlock>(), up.n_blocks, up.raw_end,
-                        c.g_wscr[slot].as<uint32_t>(), c.g_counts[slot].as<uint32_t>(), c.g_base[slot].as<uint32_t>(),
-                        c.h_total.as<uint32_t>() + slot, up.d_offs, up.end_pos, c.scalars.as<DeviceScalars>(), ws);
+            launch_walk(up.d_raw, c.g_walkers[slot].as<uint2>(), up.n_walkers, up.scheme, c.g_blocks[slot].as<InflateBlock>(), up.n_blocks,
+                        up.scheme == 1 ? nullptr : c.g_spec[slot].as<uint32_t>(), c.g_wscr[slot].as<uint32_t>(),
+                        c.g_counts[slot].as<uint32_t>(), c.g_base[slot].as<uint32_t>(), c.h_total.as<uint32_t>() + slot, up.d_offs, up.end_pos,
+                        c.scalars.as<DeviceScalars>(), ws);
             BSG_CUDA(cudaEventRecord(spw.b, ws));
             walk_spans.push_back(spw);
-            kt_.launches += (up.n_blocks ? 1 : 0) + ((up.n_walkers && up.n_blocks) ? (up.max_span <= (96u << 10) ? 3 : 5) : 1);
+            kt_.launches += (up.n_blocks ? 1 : 0) + ((up.n_walkers && up.n_blocks) ? (up.scheme == 1 ? 3 : 4) : 1);
             // (the record count lands in pinned host memory straight from the scan kernel: a 4-byte cudaMemcpy would queue
             // behind the 32 MiB result copies on the device-to-host engine - measured: up to 6 ms per batch)
             BSG_CUDA(cudaEventRecord(c.ev_total[slot], ws));

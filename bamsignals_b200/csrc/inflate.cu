@@ -36,7 +36,8 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int kWsDecWarps = 2;                       // warps whose 32 lanes decode one stream each
 constexpr int kWsStreams = kWsDecWarps * 32;         // streams resident per CTA (= per SM)
 constexpr int kWsCopyWarps = 16;                     // warps that materialise the token queues, four streams each
-constexpr int kWsThreads = (kWsDecWarps + kWsCopyWarps) * 32;
+constexpr int kWsChainWarp = kWsDecWarps + kWsCopyWarps;      // the warp that follows the record chains (SpecOut)
+constexpr int kWsThreads = (kWsDecWarps + kWsCopyWarps + 1) * 32;
 
 struct WsStream {
     inflate_core::Tables T;
@@ -131,6 +132,21 @@ struct SmemAccess {
 constexpr int kQpw = 4;                              // queues (streams) per copy warp, one after the other
 constexpr int kChunk = 256;                          // bytes staged per chunk
 constexpr int kSteps = kChunk / 32;
+
+// One more warp of the CTA, the CHAIN warp, follows every resident block's RECORD chain (block_size -> next record) right
+// behind the copy warps, one or two streams per lane: the bytes are a round old and L2-resident (~235 ns per step,
+// profiles/r2_chain_probe.txt; the same chain costs up to 500 ns per step once the batch has left the L2), a round
+// brings ~4 records per stream, and the warp has the whole round (~14 us) for them.  The record walk gets, per block, the
+// offsets of the chain that starts at the block's first byte - a speculation (a record may straddle into the block),
+// verified and linked by k_walk_link.  (Following the chain from lane 0 of the copy warps while a chunk is on the stage
+// was measured first: 8.5 -> 12.2 ms per two waves, 31 idle lanes per step.)
+struct SpecOut {
+    uint32_t* offs;        // [n_blocks][kSpecStride] absolute offsets (into the batch's raw buffer) of the chain's records
+    uint32_t* cnt;         // [n_blocks] records on the chain; kSpecNone = no usable chain (implausible record, stored block ...)
+    uint32_t* end;         // [n_blocks] where the chain first reaches or passes the block's end (absolute)
+};
+constexpr uint32_t kSpecStride = 1824;               // a record takes >= 36 bytes: at most 1821 start in a 64 KiB block
+constexpr uint32_t kSpecNone = 0xffffffffu;
 
 // One queue -> bytes at first_byte; stage = kChunk bytes of shared memory owned by the warp (8-byte aligned).
 // Returns the number of bytes.
@@ -267,7 +283,7 @@ __device__ __forceinline__ uint32_t materialise(const uint32_t* q, int nq, uint8
 }
 
 __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock* __restrict__ blocks, int n_blocks,
-                                                              const uint8_t* __restrict__ comp, uint8_t* raw, DeviceScalars* sc) {
+                                                              const uint8_t* __restrict__ comp, uint8_t* raw, SpecOut spec, DeviceScalars* sc) {
     using namespace inflate_core;
     extern __shared__ __align__(16) uint8_t ws_smem[];
     WsStream* S = reinterpret_cast<WsStream*>(ws_smem);
@@ -298,6 +314,38 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
             acc.dist_a = acc.lit_a + uint32_t(sizeof(uint16_t) << kLitBits);
         }
         const uint32_t out_len = blk.out_len;
+        // chain warp: lane l follows the chains of streams l and l + 32 of this generation
+        uint32_t c_rp[2] = {0u, 0u}, c_rn[2] = {0u, 0u}, c_len[2] = {0u, 0u}, c_off[2] = {0u, 0u};
+        if (wid == kWsChainWarp && spec.offs) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int bi = b0 + lane + 32 * h;
+                if (bi < n_blocks) { c_len[h] = blocks[bi].out_len; c_off[h] = blocks[bi].out_off; } else c_rn[h] = kSpecNone;
+            }
+        }
+        // follow both chains as far as the copy warps have come (all = true: to the end of the blocks)
+        auto chain_follow = [&](bool all) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                const uint32_t avail = all ? c_len[h] : *reinterpret_cast<volatile uint32_t*>(&ctl.pos[k]);
+                __threadfence_block();                           // the position first, then the bytes it announces
+                if (c_rn[h] == kSpecNone) continue;
+                uint32_t* row = spec.offs + size_t(b0 + k) * kSpecStride;
+                uint32_t rp = c_rp[h], rn = c_rn[h];
+                while (rp < c_len[h] && rp + 4u <= avail) {
+                    const uint32_t a = c_off[h] + rp;                                              // raw itself is aligned, blocks are not
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (a & ~3u));
+                    const uint32_t sh = (a & 3u) * 8u;
+                    const uint32_t lo = __ldcg(w), hi = sh ? __ldcg(w + 1) : 0u;                  // L2: L1 may hold the line as it was a round ago
+                    const uint32_t bs = __funnelshift_r(lo, hi, sh);
+                    if (bs < 32u || bs > 0x00ffffffu || rn >= kSpecStride) { rn = kSpecNone; break; }
+                    row[rn++] = c_off[h] + rp;
+                    rp += 4u + bs;
+                }
+                c_rp[h] = rp; c_rn[h] = rn;
+            }
+        };
         const uint64_t end_bit = (uint64_t(blk.in_off) + blk.in_len) * 8u;
         uint32_t op_dec = 0;
         int phase = 0, last = 0;
@@ -345,6 +393,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                 ctl.qn[buf][s] = uint8_t(nq);
                 const bool any = __any_sync(FULL, nq > 0);
                 if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
+            } else if (wid == kWsChainWarp) {
+                if (spec.offs) chain_follow(false);
             } else if (r > 0) {
                 // ---- the queues of the previous round -> bytes: this warp's four streams, one after the other -----------------
                 const int pb = buf ^ 1;
@@ -361,11 +411,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         const uint8_t* src = comp + q[1];
                         for (uint32_t i = lane; i < len; i += 32) out[pos + i] = src[i];
                         __syncwarp();
+                        __threadfence_block();                                      // bytes before the position that announces them (chain warp)
                         if (lane == 0) ctl.pos[k] = pos + len;
                         nq = 0;
                     }
                     if (nq > 0) {                                                  // warp-uniform
                         const uint32_t total = materialise(q, nq, out + pos, lane, stage);
+                        __threadfence_block();
                         if (lane == 0) ctl.pos[k] = pos + total;
                     }
                 }
@@ -378,6 +430,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
         }
         // every stream must have produced exactly ISIZE bytes
         if (threadIdx.x < kWsStreams && b0 + s < n_blocks && ctl.pos[s] != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
+        if (spec.offs && wid == kWsChainWarp) {                 // the rest of the chains, then what the record walk needs of them
+            chain_follow(true);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int bi = b0 + lane + 32 * h;
+                if (bi < n_blocks) {
+                    // a chain that stopped short of the block's end (its next size field straddles the end), or whose block
+                    // came out short (reported above), is no chain
+                    const bool ok = c_rn[h] != kSpecNone && c_rp[h] >= c_len[h] && ctl.pos[lane + 32 * h] == c_len[h];
+                    spec.cnt[bi] = ok ? c_rn[h] : kSpecNone;
+                    spec.end[bi] = c_off[h] + c_rp[h];
+                }
+            }
+        }
         __syncthreads();                             // the next generation re-initialises the control block
     }
 }
@@ -470,33 +536,35 @@ __device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* raw, uint32_t off)
 
 // The walk, block-parallel.  A walker is the span between two index entry points; its record chain is serial, and on deep
 // data a span holds tens of thousands of records (C4: 10.8 ms per batch for the longest chains, 2 of 32 lanes busy, the
-// bottleneck of the whole call).  BAM writers start nearly every BGZF block on a record boundary, so:
-//   k_walk_spec   one thread per BLOCK walks from the block's first byte to its end: record count, where the chain lands,
-//                 and for every entry point inside the block whether the chain passes through it and after how many
-//                 records (its RANK).  Pure speculation - but an entry point IS a record boundary: from an entry point
-//                 that lies on the block's chain onwards, that chain is the true one.
-//   k_walk_link   one thread per WALKER counts its records block by block in O(1) steps per block: first block
-//                 = (block's count - rank of its begin), blocks inside the span = their count if the chain enters them at
-//                 their first byte, last block = rank of its end.  Where speculation does not apply (a record straddling
-//                 into a block, an entry point off the block's chain) it walks that piece itself.
+// bottleneck of the whole call) - and a step of such a chain through global memory costs 235-500 ns.  BAM writers start
+// nearly every BGZF block on a record boundary, and the inflate kernel has followed, for every block, the chain that
+// starts at the block's first byte while the block went through shared memory (SpecOut).  That chain is a speculation
+// - a record may straddle into the block - but an entry point IS a record boundary: from an entry point that lies on the
+// block's chain onwards, that chain is the true one.  So:
+//   k_walk_link   one thread per WALKER counts its records block by block in O(1) per block (binary searches in the
+//                 blocks' chains): first block = (block's count - rank of the span's begin), blocks inside the span =
+//                 their count if the true chain enters them at their first byte, last block = rank of the span's end.
+//                 Where speculation does not apply (a record straddling into a block, an entry point off the block's
+//                 chain, a block without a chain) it walks that piece itself.
 //   k_scan_counts bases of the walkers in the offsets array.
-//   k_walk_write  one thread per block writes the offsets of its chain: records from an on-chain entry point j onwards go to
-//                 base[j] + (rank - rank of j), those before the first entry point continue the walker in front if the chain
-//                 truly entered the block at its first byte; one thread per walker writes the pieces it had to walk itself.
-// Every chain any thread walks is at most one block long (~1200 records).
+//   k_walk_write  one thread per block copies the offsets of its chain: records from an on-chain entry point j onwards go
+//                 to base[j] + (rank - rank of j), those before the first entry point continue the walker in front if the
+//                 chain truly entered the block at its first byte; one thread per walker writes the pieces it walked itself.
+// On htslib-written files no thread follows a chain through global memory at all.
 struct WalkScratch {       // per batch; n_blocks / n_walkers entries each
-    uint32_t* spec_cnt;    // block: records on its speculative chain; kSpecBad = the chain ran into an implausible record
-    uint32_t* spec_end;    // block: where that chain first reaches or passes the block's end
+    const uint32_t* spec_cnt;   // block: records on its speculative chain (kSpecNone: no usable chain); from the inflate kernel
+    const uint32_t* spec_end;   // block: where that chain first reaches or passes the block's end
+    const uint32_t* spec_offs;  // block: [kSpecStride] the chain's record offsets
     uint32_t* entry;       // block inside a span: where the true chain enters it; with owner / first set by k_walk_link
     uint32_t* first;       // ... how many records of its walker come before it
     uint32_t* owner;       // ... and the walker (kNoOwner: not inside one span)
     uint32_t* entry_true;  // block: 1 = the true chain enters it exactly at its first byte
-    uint32_t* rank;        // walker: rank of its begin on its block's speculative chain (kSpecBad = not on it)
+    uint32_t* rank;        // walker: rank of its begin on its block's speculative chain (kSpecNone = not on it)
     uint32_t* self_first;  // walker: 1 = it walked (and writes) its piece of its first block itself
     uint32_t* last_entry;  // walker: entry + records before of a last, partial block it walked itself (kNoOwner = none)
     uint32_t* last_first;
 };
-constexpr uint32_t kSpecBad = 0xffffffffu, kNoOwner = 0xffffffffu;
+constexpr uint32_t kNoOwner = 0xffffffffu;
 
 // A chain only moves forward, one dependent load per record, ~50 bytes further on every time - and caches fill by 32-byte
 // SECTOR, so unassisted every step is a trip to DRAM of its own (the bytes were inflated a moment ago, a batch is several
@@ -531,9 +599,8 @@ __device__ __forceinline__ bool walk_step(const uint8_t* raw, uint32_t& p, uint3
     return true;
 }
 
-// The simple scheme, used when no span is longer than a block (launch_walk decides): one thread per walker counts its
-// records, a scan, the same walk again writes the offsets.  Two chains of at most a block each and no per-block passes:
-// on C2 (16 kb index windows, ~500 records per span) a third of the block-parallel scheme's device time.
+// The simple scheme (opts.walk_scheme = 1, or no chains from the inflate kernel): one thread per walker counts its
+// records, a scan, the same walk again writes the offsets: two chains through global memory per span.
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_walk_span(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
                                                    uint32_t* __restrict__ counts, const uint32_t* __restrict__ base,
@@ -575,34 +642,17 @@ __device__ __forceinline__ int block_of(const InflateBlock* __restrict__ blocks,
     return lo;
 }
 
-__global__ void __launch_bounds__(128) k_walk_spec(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
-                                                   const InflateBlock* __restrict__ blocks, int n_blocks, uint32_t raw_end, WalkScratch ws) {
-    const int b = blockIdx.x * 128 + threadIdx.x;
-    if (b >= n_blocks) return;
-    const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
-    int j = first_walker_at_or_after(walkers, n_walkers, s0);         // entry points inside the block: walkers[j..] while < e0
-    uint32_t next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
-    uint32_t p = s0, n = 0;
-    bool ok = true;
-    walk_prefetch_start(raw, p, raw_end);
-    while (p < e0) {
-        while (next <= p) {                                           // an entry point reached (rank n) or jumped over
-            ws.rank[j] = next == p ? n : kSpecBad;
-            ++j;
-            next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
-        }
-        if (!walk_step(raw, p, raw_end)) { ok = false; break; }
-        ++n;
+// rank of position x on block b's speculative chain (kSpecNone = not on it)
+__device__ __forceinline__ uint32_t rank_on_chain(const WalkScratch& ws, int b, uint32_t x) {
+    const uint32_t n = ws.spec_cnt[b];
+    if (n == kSpecNone) return kSpecNone;
+    const uint32_t* o = ws.spec_offs + size_t(b) * kSpecStride;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (o[mid] < x) lo = mid + 1; else hi = mid;
     }
-    for (; next != 0xffffffffu; ) {                                   // entry points behind a chain that broke off
-        ws.rank[j] = kSpecBad;
-        ++j;
-        next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
-    }
-    ws.spec_cnt[b] = ok ? n : kSpecBad;
-    ws.spec_end[b] = p;
-    ws.owner[b] = kNoOwner;
-    ws.entry_true[b] = 0u;
+    return (lo < n && o[lo] == x) ? lo : kSpecNone;
 }
 
 __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ raw, const uint2* __restrict__ walkers, int n_walkers,
@@ -611,20 +661,24 @@ __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ r
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= n_walkers) return;
     const uint32_t wb = walkers[w].x, we = walkers[w].y;
-    // is the walker's end an entry point on the speculative chain of its block?  (then rank[w + 1] counts the records of
-    // that block in front of it)
-    const bool end_ranked = w + 1 < n_walkers && walkers[w + 1].x == we && ws.rank[w + 1] != kSpecBad;
     int b = block_of(blocks, n_blocks, wb);
     uint32_t p = wb, n = 0;
     bool bad = false;
     ws.last_entry[w] = kNoOwner;
     ws.self_first[w] = 0u;
+    ws.rank[w] = kSpecNone;
+    // rank of the span's END on the chain of the block that holds it (the next walker's begin, when the spans touch):
+    // looked up only where it is needed
+    const bool end_is_entry = w + 1 < n_walkers && walkers[w + 1].x == we;
     if (p < we && p != blocks[b].out_off) {
         // the span begins inside a block
         const uint32_t e0 = blocks[b].out_off + blocks[b].out_len;
-        const uint32_t r0 = ws.rank[w];
-        if (r0 != kSpecBad && e0 <= we && ws.spec_cnt[b] != kSpecBad) { n = ws.spec_cnt[b] - r0; p = ws.spec_end[b]; }
-        else if (r0 != kSpecBad && e0 > we && end_ranked) { n = ws.rank[w + 1] - r0; p = we; }
+        const uint32_t r0 = rank_on_chain(ws, b, wb);
+        ws.rank[w] = r0;
+        uint32_t r1 = kSpecNone;
+        if (r0 != kSpecNone && e0 > we && end_is_entry) r1 = rank_on_chain(ws, b, we);
+        if (r0 != kSpecNone && e0 <= we) { n = ws.spec_cnt[b] - r0; p = ws.spec_end[b]; }
+        else if (r1 != kSpecNone) { n = r1 - r0; p = we; }
         else {
             ws.self_first[w] = 1u;
             const uint32_t stop = min(e0, we);
@@ -634,18 +688,19 @@ __global__ void __launch_bounds__(128) k_walk_link(const uint8_t* __restrict__ r
                 ++n;
             }
         }
-    }
+    } else if (p < we) ws.rank[w] = ws.spec_cnt[b] != kSpecNone ? 0u : kSpecNone;      // begins at a block's first byte
     while (p < we && !bad) {
         while (b + 1 < n_blocks && blocks[b + 1].out_off <= p) ++b;
         const uint32_t s0 = blocks[b].out_off, e0 = s0 + blocks[b].out_len;
         if (p >= e0) { bad = true; break; }     // padding between two segments of the batch: no span crosses it
         if (p == s0) ws.entry_true[b] = 1u;
-        const bool spec_ok = p == s0 && ws.spec_cnt[b] != kSpecBad;
+        const bool spec_ok = p == s0 && ws.spec_cnt[b] != kSpecNone;
         if (e0 <= we) {                         // the block lies inside the span
             ws.entry[b] = p; ws.first[b] = n; ws.owner[b] = uint32_t(w);
             if (spec_ok) { n += ws.spec_cnt[b]; p = ws.spec_end[b]; continue; }
         } else {                                // the span ends inside this block
-            if (spec_ok && end_ranked) { n += ws.rank[w + 1]; p = we; continue; }
+            const uint32_t r1 = (spec_ok && end_is_entry) ? rank_on_chain(ws, b, we) : kSpecNone;
+            if (r1 != kSpecNone) { n += r1; p = we; continue; }
             ws.last_entry[w] = p; ws.last_first[w] = n;
         }
         const uint32_t stop = min(e0, we);
@@ -669,11 +724,17 @@ __global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ 
     if (BLOCK) {
         if (i >= n_blocks) return;
         const uint32_t s0 = blocks[i].out_off, e0 = s0 + blocks[i].out_len;
-        if (ws.owner[i] != kNoOwner) {                  // inside one span: from where the true chain enters it
+        const uint32_t cnt = ws.spec_cnt[i];
+        const uint32_t* so = ws.spec_offs + size_t(i) * kSpecStride;
+        if (ws.owner[i] != kNoOwner) {                  // inside one span
             const uint32_t w = ws.owner[i], lim = walkers[w].y;
-            uint32_t p = ws.entry[i];
             uint32_t* o = offs + base[w] + ws.first[i];
-            walk_prefetch_start(raw, p, lim);
+            uint32_t p = ws.entry[i];
+            if (p == s0 && cnt != kSpecNone) {           // its chain is the true one: a copy
+                for (uint32_t r = 0; r < cnt; ++r) o[r] = so[r];
+                return;
+            }
+            walk_prefetch_start(raw, p, lim);           // entered behind its first byte: from where the true chain enters it
             while (p < e0) {
                 *o++ = p;
                 if (!walk_step(raw, p, lim)) break;     // (validated by k_walk_link; never taken)
@@ -681,16 +742,15 @@ __global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ 
             return;
         }
         // a block with entry points inside: its speculative chain, attributed walker by walker
+        if (cnt == kSpecNone) return;
         int j = first_walker_at_or_after(walkers, n_walkers, s0);
         if (j >= n_walkers || walkers[j].x >= e0) return;
         uint32_t next = walkers[j].x;
         // records in front of the first entry point continue the walker before it - if the chain truly entered at s0
-        bool live = ws.entry_true[i] != 0u && ws.rank[j] != kSpecBad && j > 0 && walkers[j - 1].y == next;
+        bool live = ws.entry_true[i] != 0u && ws.rank[j] != kSpecNone && j > 0 && walkers[j - 1].y == next;
         uint32_t idx0 = live ? base[j] - ws.rank[j] : 0u, lim = next;      // offs index of the chain's record 0; end of the current walker
-        uint32_t p = s0, n = 0;
-        const uint32_t raw_end = blocks[n_blocks - 1].out_off + blocks[n_blocks - 1].out_len;
-        walk_prefetch_start(raw, p, raw_end);
-        while (p < e0) {
+        for (uint32_t n = 0; n < cnt; ++n) {
+            const uint32_t p = so[n];
             while (next <= p) {
                 if (next == p && ws.rank[j] == n) { live = true; idx0 = base[j] - n; lim = walkers[j].y; }
                 else live = false;                      // an entry point off the chain: what follows is not verified
@@ -699,8 +759,6 @@ __global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ 
             }
             if (live && p >= lim) live = false;         // behind the last walker of a segment
             if (live) offs[idx0 + n] = p;
-            if (!walk_step(raw, p, raw_end)) break;
-            ++n;
         }
     } else {
         if (i >= n_walkers) return;
@@ -778,7 +836,7 @@ __global__ void __launch_bounds__(32) k_scan_counts(const uint32_t* __restrict__
 
 }  // namespace
 
-void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
+void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, uint32_t* d_spec, DeviceScalars* sc,
                     cudaStream_t s) {
     if (n_blocks <= 0) return;
     static thread_local int sms[16] = {};
@@ -790,8 +848,11 @@ void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d
     }
     const int n_sm = (dev >= 0 && dev < 16 && sms[dev] > 0) ? sms[dev] : 148;
     const int grid = std::min(n_sm, (n_blocks + kWsStreams - 1) / kWsStreams);     // persistent: one CTA per SM
-    k_inflate_ws<<<grid, kWsThreads, kWsSmem, s>>>(d_blocks, n_blocks, d_comp, d_raw, sc);
+    SpecOut spec{nullptr, nullptr, nullptr};
+    if (d_spec) { spec.cnt = d_spec; spec.end = d_spec + n_blocks; spec.offs = d_spec + 2 * size_t(n_blocks); }
+    k_inflate_ws<<<grid, kWsThreads, kWsSmem, s>>>(d_blocks, n_blocks, d_comp, d_raw, spec, sc);
 }
+size_t inflate_spec_words(int n_blocks) { return size_t(n_blocks) * (2 + kSpecStride) + 16; }
 
 int inflate_wave_blocks(int n_sm) { return n_sm * kWsStreams; }
 
@@ -817,32 +878,32 @@ void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blo
     k_crc32<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s>>>(d_blocks, d_crc, n_blocks, d_raw, sc);
 }
 
-constexpr uint32_t kSpanSimple = 96u << 10;     // spans up to this many bytes: the simple per-walker scheme
-void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t max_span, const InflateBlock* d_blocks, int n_blocks,
-                 uint32_t raw_end, uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs, uint32_t end_pos,
-                 DeviceScalars* sc, cudaStream_t s) {
+void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, int scheme, const InflateBlock* d_blocks, int n_blocks,
+                 const uint32_t* d_spec, uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs,
+                 uint32_t end_pos, DeviceScalars* sc, cudaStream_t s) {
     if (n_walkers <= 0 || n_blocks <= 0) {
         k_scan_counts<<<1, 32, 0, s>>>(d_counts, 0, d_base, d_total, d_offs, end_pos);
         return;
     }
     const int gb = (n_blocks + 127) / 128, gw = (n_walkers + 127) / 128;
-    if (max_span <= kSpanSimple) {
+    if (scheme == 1 || !d_spec) {
         k_walk_span<false><<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_counts, nullptr, nullptr, sc);
         k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
         k_walk_span<true><<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, nullptr, d_base, d_offs, sc);
         return;
     }
     WalkScratch ws;
-    ws.spec_cnt = d_scratch; ws.spec_end = ws.spec_cnt + n_blocks; ws.entry = ws.spec_end + n_blocks; ws.first = ws.entry + n_blocks;
-    ws.owner = ws.first + n_blocks; ws.entry_true = ws.owner + n_blocks;
-    ws.rank = ws.entry_true + n_blocks; ws.self_first = ws.rank + n_walkers; ws.last_entry = ws.self_first + n_walkers;
+    ws.spec_cnt = d_spec; ws.spec_end = d_spec + n_blocks; ws.spec_offs = d_spec + 2 * size_t(n_blocks);
+    ws.owner = d_scratch; ws.entry_true = ws.owner + n_blocks; ws.entry = ws.entry_true + n_blocks; ws.first = ws.entry + n_blocks;
+    ws.rank = ws.first + n_blocks; ws.self_first = ws.rank + n_walkers; ws.last_entry = ws.self_first + n_walkers;
     ws.last_first = ws.last_entry + n_walkers;
-    k_walk_spec<<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, raw_end, ws);
+    cudaMemsetAsync(ws.owner, 0xff, size_t(n_blocks) * 4, s);
+    cudaMemsetAsync(ws.entry_true, 0, size_t(n_blocks) * 4, s);
     k_walk_link<<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_counts, ws, sc);
     k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
     k_walk_write<true><<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
     k_walk_write<false><<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);
 }
-size_t walk_scratch_words(int n_blocks, int n_walkers) { return size_t(n_blocks) * 6 + size_t(n_walkers) * 4 + 16; }
+size_t walk_scratch_words(int n_blocks, int n_walkers) { return size_t(n_blocks) * 4 + size_t(n_walkers) * 4 + 16; }
 
 }  // namespace bsg

@@ -84,8 +84,12 @@ struct InflateBlock {
     uint32_t out_off;   // byte offset in the batch's raw buffer
     uint32_t out_len;   // ISIZE
 };
-void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, DeviceScalars* sc,
+// d_spec (inflate_spec_words(n_blocks) uint32 of device memory, or null): per block, the record chain that starts at the
+// block's first byte, followed while the block passes through shared memory: [n_blocks] record counts (0xffffffff = no
+// usable chain), [n_blocks] where the chain lands, [n_blocks][1824] the records' offsets.  launch_walk links them.
+void launch_inflate(const InflateBlock* d_blocks, int n_blocks, const uint8_t* d_comp, uint8_t* d_raw, uint32_t* d_spec, DeviceScalars* sc,
                     cudaStream_t s);
+size_t inflate_spec_words(int n_blocks);
 // BGZF blocks one launch keeps in flight on a device with n_sm SMs: batches that are a multiple of this leave no partly
 // filled last generation.
 int inflate_wave_blocks(int n_sm);
@@ -93,11 +97,12 @@ int inflate_wave_blocks(int n_sm);
 void launch_crc32(const InflateBlock* d_blocks, const uint32_t* d_crc, int n_blocks, const uint8_t* d_raw, DeviceScalars* sc,
                   cudaStream_t s);
 // Record-boundary walk between index entry points: walkers[w] = (begin, end) byte positions in d_raw, both record
-// boundaries, each inside one run of consecutive blocks (d_blocks[0..n_blocks) in out_off order; raw_end = end of the last
-// one); max_span = the longest walker in bytes (short spans take a simpler scheme).  Fills d_offs[0..total] (+ end
-// sentinel) and *d_total; d_scratch: walk_scratch_words() uint32 of device memory.
-void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, uint32_t max_span, const InflateBlock* d_blocks, int n_blocks,
-                 uint32_t raw_end, uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs,
+// boundaries, each inside one run of consecutive blocks (d_blocks[0..n_blocks) in out_off order).  scheme 1 (or d_spec
+// null): every span's chain is followed through global memory, twice; otherwise the spans are linked through the
+// per-block chains the inflate kernel left in d_spec (launch_inflate) and only what those cannot cover is walked.
+// Fills d_offs[0..total] (+ end sentinel) and *d_total; d_scratch: walk_scratch_words() uint32 of device memory.
+void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, int scheme, const InflateBlock* d_blocks, int n_blocks,
+                 const uint32_t* d_spec, uint32_t* d_scratch, uint32_t* d_counts, uint32_t* d_base, uint32_t* d_total, uint32_t* d_offs,
                  uint32_t end_pos, DeviceScalars* sc, cudaStream_t s);
 size_t walk_scratch_words(int n_blocks, int n_walkers);
 

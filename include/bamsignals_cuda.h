@@ -81,9 +81,11 @@ typedef struct bsg_opts {
                                  scatters them into the caller's buffers (a portion with too many such elements travels
                                  as int32); -1 = always int32; N > 0 = as 0 with room for one pair per N elements
                                  (default 64) */
-    int32_t walk_scheme;      /* device record walk between index entry points: 0 (default) = per span when no span of
-                                 the batch exceeds 96 KiB, else block-parallel (speculative chain per BGZF block, spans
-                                 linked through the blocks); 1 / 2 force the one / the other */
+    int32_t walk_scheme;      /* device record walk between index entry points: 1 = every span's record chain is followed
+                                 through device memory (count, scan, write); 2 = spans are linked through per-block
+                                 chains that the inflate kernel follows while the blocks are L2-resident, and only what
+                                 those cannot cover is walked; 0 (default) = 1 when no span of the batch exceeds 96 KiB,
+                                 else 2 */
     int32_t reserved[5];
 } bsg_opts;
 

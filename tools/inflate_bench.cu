@@ -3,7 +3,7 @@
 // kernel is the correctness check (every block against its BGZF trailer).  The kernel source is compiled INTO this
 // binary, so that variants (-D switches) can be built side by side and measured in one GPU call:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --use_fast_math -lineinfo [-D...] -o inflate_bench tools/inflate_bench.cu
-//   inflate_bench file.bam [max_blocks (0 = two waves)] [reps]
+//   inflate_bench file.bam [max_blocks (0 = two waves)] [reps] [spec: 1 = also follow the record chains]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +20,7 @@ int main(int argc, char** argv) {
     long max_blocks = argc > 2 ? atol(argv[2]) : 0;
     if (max_blocks <= 0) max_blocks = 2L * bsg::inflate_wave_blocks(n_sm);
     const int reps = argc > 3 ? atoi(argv[3]) : 5;
+    const bool want_spec = argc > 4 && atoi(argv[4]) != 0;
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 1; }
     fseek(f, 0, SEEK_END);
@@ -62,6 +63,8 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_comp, d.data() + first, comp_bytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_blocks, blocks.data(), blocks.size() * sizeof(bsg::InflateBlock), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_crc, crcs.data(), crcs.size() * 4, cudaMemcpyHostToDevice));
+    uint32_t* d_spec = nullptr;
+    if (want_spec) CK(cudaMalloc(&d_spec, bsg::inflate_spec_words(int(blocks.size())) * 4));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -69,7 +72,7 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 1; ++r) {
         CK(cudaMemsetAsync(d_raw, 0xA5, out, 0));                      // also evicts the previous run's output from L2
         CK(cudaEventRecord(e0, 0));
-        bsg::launch_inflate(d_blocks, int(blocks.size()), d_comp, d_raw, d_sc, 0);
+        bsg::launch_inflate(d_blocks, int(blocks.size()), d_comp, d_raw, d_spec, d_sc, 0);
         CK(cudaEventRecord(e1, 0));
         bsg::launch_crc32(d_blocks, d_crc, int(blocks.size()), d_raw, d_sc, 0);
         CK(cudaDeviceSynchronize());
@@ -79,6 +82,13 @@ int main(int argc, char** argv) {
     }
     bsg::DeviceScalars sc;
     CK(cudaMemcpy(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (d_spec) {       // how many blocks got a chain, how many records
+        std::vector<uint32_t> cnt(blocks.size());
+        CK(cudaMemcpy(cnt.data(), d_spec, blocks.size() * 4, cudaMemcpyDeviceToHost));
+        size_t ok = 0; uint64_t recs = 0;
+        for (uint32_t c : cnt) if (c != 0xffffffffu) { ++ok; recs += c; }
+        printf("spec: %zu of %zu blocks have a chain, %llu records\n", ok, blocks.size(), (unsigned long long)recs);
+    }
     printf("{\"blocks\": %zu, \"comp_mb\": %.1f, \"out_mb\": %.1f, \"ms_min\": %.3f, \"ms_mean\": %.3f, \"out_gbs\": %.1f, \"status\": %u}\n",
            blocks.size(), comp_bytes / 1e6, out / 1e6, best, sum / reps, out / 1e6 / best, sc.status);
     return sc.status ? 3 : 0;

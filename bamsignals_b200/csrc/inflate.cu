@@ -129,7 +129,9 @@ struct SmemAccess {
 // chased through the 128 bytes of the step only: 5.5 rounds, 8.7 ms; one byte per lane, load -> store -> next step, four
 // queues interleaved per warp: 6.6 ms, then 5.5 ms with the faster decode side, the copy warps the bottleneck again
 // (half of the L2 reads miss: the 32 KiB windows of 9472 streams are 2.5x the L2, so every step waited for DRAM).
-constexpr int kQpw = 4;                              // queues (streams) per copy warp, one after the other
+constexpr int kQpw = 4;                              // queues (streams) per copy warp, one after the other (taking them
+                                                     // dynamically, one atomic per queue: measured, 8.69 vs 8.50 ms - dropped;
+                                                     // so was a second-level table for long DISTANCE codes: 8.55 vs 8.50)
 constexpr int kChunk = 256;                          // bytes staged per chunk
 constexpr int kSteps = kChunk / 32;
 

@@ -111,14 +111,23 @@ def region_result(res, i):
     return np.asarray(res[int(i)]).ravel(order="F")
 
 
-def check_prefix(res, gr, fn, kw, bam, budget_s, threads, want=None):
+def check_prefix(res, gr, fn, kw, bam, budget_s, threads, want=None, full=False):
     """Compare the first regions (genomic order) of `res` - the result of a timed call over `gr` - bit for bit with the CPU
-    checker.  `want` = (k, checker result over the first k regions) when the caller already has one (cpu_baseline)."""
+    checker.  `want` = (k, checker result over the first k regions) when the caller already has one (cpu_baseline);
+    full: every region of the job."""
     kind, O = checker()
     n = len(gr)
     if n == 0:
         return {"regions_checked": 0, "equal": True, "checker": kind}
     order = np.lexsort((gr.start, gr.seq_idx))
+    if full:
+        t0 = time.perf_counter()
+        w = getattr(O, fn)(bam, gr, nthreads=threads, impl=kind, **kw)
+        dt = time.perf_counter() - t0
+        a, b = WL.as_flat(res), WL.as_flat(w)
+        ok = a.shape == b.shape and bool(np.array_equal(a, b))
+        return {"regions_checked": int(n), "ints_checked": int(a.size), "equal": ok, "checker": kind, "checker_threads": threads,
+                "checker_seconds": round(dt, 2)}
     if want is None:
         k0 = max(1, min(n, n // 200 if n > 400 else max(1, n // 8)))
         t0 = time.perf_counter()
@@ -247,6 +256,12 @@ def measure_ours(args, preset, gs, rank, world, local_rank, dist, barrier, sampl
         cpu, want = cpu_baseline(bam, gr_all, fn, kw, threads=1, budget_s=args.cpu_seconds, total_reads=units)
         out["cpu"] = cpu
         out["parity"] = check_prefix(res, gr, fn, kw, bam, 0, 1, want=want)
+        del want
+        # the WHOLE timed result against the checker on all host threads, when that fits the budget (C2: ~1 s, C4: ~15 s)
+        est = units / max(1.0, cpu["value"] * max(1.0, 0.6 * host_threads))
+        if out["parity"]["equal"] and args.full_parity_seconds > 0 and est <= args.full_parity_seconds:
+            out["parity"]["full"] = check_prefix(res, gr, fn, kw, bam, 0, host_threads, full=True)
+            out["parity"]["equal"] = out["parity"]["equal"] and out["parity"]["full"]["equal"]
     else:
         out["parity"] = check_prefix(res, gr, fn, kw, bam, args.parity_seconds, host_threads)
         if rank == 0:
@@ -366,6 +381,9 @@ def reduce_and_format(args, m, rank, world, dist, torch):
         line["parity"] = {"equal": mins[0] > 0, "regions_checked": int(p_regions), "ints_checked": int(p_ints),
                           "checker": m["parity"]["checker"],
                           "what": "result of the last timed e2e call vs the CPU checker, a genomic prefix of every rank's regions"}
+        if "full" in m["parity"]:
+            line["parity"]["full"] = m["parity"]["full"]
+            line["parity"]["what"] += "; full = EVERY region of that result vs the checker on all host threads"
         if "cpu" in m:
             line["cpu_baseline"] = m["cpu"]
     return line, mins[0] > 0
@@ -601,6 +619,8 @@ def main():
                     "reference's fixture) and presets; default c1,c4 at gscale 1, c1 otherwise; 'none' to skip")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--full-parity-seconds", type=float, default=40.0, help="N = 1: also compare EVERY region of the timed result "
+                    "with the checker on all host threads when that is estimated to take no longer than this (0 = off)")
     ap.add_argument("--parity-seconds", type=float, default=4.0, help="CPU-checker budget per rank for the parity check (N > 1)")
     ap.add_argument("--gpu-inflate", type=int, default=1, help="1: inflate BGZF on the GPU (default), 0: host zlib pool")
     ap.add_argument("--profile", action="store_true", help="resident steps only (for runs under ncu)")

@@ -45,10 +45,10 @@ ncu --set full --import-source on --clock-control none -k regex:k_profile -c 1 -
     python bench.py --gscale 0.2 --steps 1 --warmup 1 --profile > $O/${TAG}_ncu_e.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_coverage -c 1 -f -o $O/${TAG}_k_coverage_c3_g0.2 \
     python bench.py --preset c3 --gscale 0.2 --steps 1 --warmup 1 --profile > $O/${TAG}_ncu_f.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:k_walk_spec -s 2 -c 1 -f -o $O/${TAG}_k_walk_spec_c4_g0.1 \
+ncu --set full --import-source on --clock-control none -k regex:k_walk_link -s 2 -c 1 -f -o $O/${TAG}_k_walk_link_c4_g0.1 \
     python tools/e2e_ab.py --preset c4 --gscale 0.1 --reps -1 base: > $O/${TAG}_ncu_g.log 2>&1
 # sanitizers on every kernel of the path (toy BAM)
 timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > $O/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/${TAG}_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > $O/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/${TAG}_racecheck.log
-tail -3 $O/${TAG}_memcheck.log $O/${TAG}_racecheck.log
+tail -n 3 $O/${TAG}_memcheck.log; tail -n 3 $O/${TAG}_racecheck.log
 ls -la $O | grep ${TAG} | wc -l

@@ -92,7 +92,7 @@ struct DeviceCtx {
     int dev = 0;
     int n_sm = 148;
     bool init = false;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_walk = nullptr, s_d2h = nullptr, s_hi = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_walk = nullptr, s_walk2 = nullptr, s_d2h = nullptr, s_hi = nullptr;
     DevBuf d_raw[kSlots], d_offs[kSlots];
     PinBuf h_raw[kSlots], h_offs[kSlots];
     cudaEvent_t ev_h2d[kSlots] = {}, ev_free[kSlots] = {};
@@ -118,6 +118,7 @@ struct DeviceCtx {
         BSG_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_aux, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_walk, cudaStreamNonBlocking));
+        BSG_CUDA(cudaStreamCreateWithFlags(&s_walk2, cudaStreamNonBlocking));
         BSG_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
         {   // decode + count kernels of finished batches overtake the inflate of the next one
             int lo_p = 0, hi_p = 0;
@@ -180,7 +181,7 @@ struct DeviceCtx {
         g_total.release(); h_total.release();
         for (auto e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear(); ev_next = 0;
-        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_walk); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
+        cudaStreamDestroy(s_copy); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_aux); cudaStreamDestroy(s_walk); cudaStreamDestroy(s_walk2); cudaStreamDestroy(s_d2h); cudaStreamDestroy(s_hi); cudaEventDestroy(ev_order);
         init = false;
     }
 };
@@ -1398,7 +1399,8 @@ private:
             // which is queued right behind this batch's inflate.  (Round 1: walk between two inflates on the compute stream,
             // 1.3 ms of every 5.7 ms batch period with the SMs nearly idle; on another stream it could not start at all while
             // an inflate launch held every SM.)
-            cudaStream_t ws = c.s_walk;
+            cudaStream_t ws = (bi & 1) ? c.s_walk2 : c.s_walk;       // two streams: on deep data a walk outlasts an inflate launch, and the
+                                                                     // walks of consecutive batches are independent chains of dependent loads
             BSG_CUDA(cudaStreamWaitEvent(ws, c.ev_inflated[slot], 0));
             Span spw{c.timing_event(), c.timing_event()};
             BSG_CUDA(cudaEventRecord(spw.a, ws));
@@ -1474,12 +1476,13 @@ private:
             }
         } catch (...) {
             // queued copies and kernels still reference this call's buffers
-            cudaStreamSynchronize(c.s_copy); cudaStreamSynchronize(c.s_comp); cudaStreamSynchronize(c.s_walk);
+            cudaStreamSynchronize(c.s_copy); cudaStreamSynchronize(c.s_comp); cudaStreamSynchronize(c.s_walk); cudaStreamSynchronize(c.s_walk2);
             cudaStreamSynchronize(c.s_aux); cudaStreamSynchronize(c.s_hi);
             throw;
         }
         BSG_CUDA(cudaStreamSynchronize(c.s_comp));
         BSG_CUDA(cudaStreamSynchronize(c.s_walk));
+        BSG_CUDA(cudaStreamSynchronize(c.s_walk2));
         BSG_CUDA(cudaStreamSynchronize(c.s_hi));
         if (opts_.verify_crc) BSG_CUDA(cudaStreamSynchronize(c.s_aux));
         tm_.ms_inflate_gpu = sum_ms(inflate_spans);

@@ -325,13 +325,27 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                 if (bi < n_blocks) { c_len[h] = blocks[bi].out_len; c_off[h] = blocks[bi].out_off; } else c_rn[h] = kSpecNone;
             }
         }
-        // follow both chains as far as the copy warps have come (all = true: to the end of the blocks)
-        auto chain_follow = [&](bool all) {
+        // Follow both chains as far as the bytes are known to be written (all = true: to the end of the blocks).  The warp
+        // learns how far that is without reading anything another warp writes in the same round: in round r the copy
+        // warps turn the queues of round r - 1 into bytes, so the chain warp adds up the token lengths of those queues
+        // (read-only in this round) and may, one round later, read that many bytes more.
+        uint32_t c_avail[2] = {0u, 0u}, c_pend[2] = {0u, 0u};
+        auto chain_follow = [&](bool all, int pb, bool have_q) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = lane + 32 * h;
-                const uint32_t avail = all ? c_len[h] : *reinterpret_cast<volatile uint32_t*>(&ctl.pos[k]);
-                __threadfence_block();                           // the position first, then the bytes it announces
+                if (!all) {
+                    c_avail[h] += c_pend[h];
+                    uint32_t sum = 0;
+                    if (have_q) {
+                        const int nq = int(ctl.qn[pb][k]);
+                        const uint32_t* q = S[k].q[pb];
+                        if (nq == 2 && !(q[0] >> 31) && (q[0] & kTokSkip)) sum = q[0] & 0xffffu;
+                        else for (int i = 0; i < nq; ++i) { const uint32_t t = q[i]; sum += (t >> 31) ? (t & 0x1ffu) : 1u; }
+                    }
+                    c_pend[h] = sum;
+                }
+                const uint32_t avail = all ? c_len[h] : c_avail[h];
                 if (c_rn[h] == kSpecNone) continue;
                 uint32_t* row = spec.offs + size_t(b0 + k) * kSpecStride;
                 uint32_t rp = c_rp[h], rn = c_rn[h];
@@ -396,7 +410,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                 const bool any = __any_sync(FULL, nq > 0);
                 if (lane == 0) ctl.produced[buf][wid] = any ? 1u : 0u;
             } else if (wid == kWsChainWarp) {
-                if (spec.offs) chain_follow(false);
+                if (spec.offs) chain_follow(false, buf ^ 1, r > 0);
             } else if (r > 0) {
                 // ---- the queues of the previous round -> bytes: this warp's four streams, one after the other -----------------
                 const int pb = buf ^ 1;
@@ -413,13 +427,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
                         const uint8_t* src = comp + q[1];
                         for (uint32_t i = lane; i < len; i += 32) out[pos + i] = src[i];
                         __syncwarp();
-                        __threadfence_block();                                      // bytes before the position that announces them (chain warp)
                         if (lane == 0) ctl.pos[k] = pos + len;
                         nq = 0;
                     }
                     if (nq > 0) {                                                  // warp-uniform
                         const uint32_t total = materialise(q, nq, out + pos, lane, stage);
-                        __threadfence_block();
                         if (lane == 0) ctl.pos[k] = pos + total;
                     }
                 }
@@ -433,7 +445,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_inflate_ws(const InflateBlock
         // every stream must have produced exactly ISIZE bytes
         if (threadIdx.x < kWsStreams && b0 + s < n_blocks && ctl.pos[s] != out_len) atomicOr(&sc->status, STATUS_BAD_DEFLATE);
         if (spec.offs && wid == kWsChainWarp) {                 // the rest of the chains, then what the record walk needs of them
-            chain_follow(true);
+            chain_follow(true, 0, false);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int bi = b0 + lane + 32 * h;
@@ -644,6 +656,11 @@ __device__ __forceinline__ int block_of(const InflateBlock* __restrict__ blocks,
     return lo;
 }
 
+__global__ void __launch_bounds__(128) k_walk_init(int n_blocks, WalkScratch ws) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b < n_blocks) { ws.owner[b] = kNoOwner; ws.entry_true[b] = 0u; }
+}
+
 // rank of position x on block b's speculative chain (kSpecNone = not on it)
 __device__ __forceinline__ uint32_t rank_on_chain(const WalkScratch& ws, int b, uint32_t x) {
     const uint32_t n = ws.spec_cnt[b];
@@ -751,16 +768,24 @@ __global__ void __launch_bounds__(128) k_walk_write(const uint8_t* __restrict__ 
         // records in front of the first entry point continue the walker before it - if the chain truly entered at s0
         bool live = ws.entry_true[i] != 0u && ws.rank[j] != kSpecNone && j > 0 && walkers[j - 1].y == next;
         uint32_t idx0 = live ? base[j] - ws.rank[j] : 0u, lim = next;      // offs index of the chain's record 0; end of the current walker
-        for (uint32_t n = 0; n < cnt; ++n) {
-            const uint32_t p = so[n];
-            while (next <= p) {
-                if (next == p && ws.rank[j] == n) { live = true; idx0 = base[j] - n; lim = walkers[j].y; }
-                else live = false;                      // an entry point off the chain: what follows is not verified
-                ++j;
-                next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
+        for (uint32_t n0 = 0; n0 < cnt; n0 += 8) {      // eight offsets per step: their loads are independent (one by one, every
+            uint32_t pv[8];                              // record cost an L2 round trip, as if the chain were being chased)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pv[u] = n0 + u < cnt ? so[n0 + u] : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t n = n0 + u, p = pv[u];
+                if (n < cnt) {
+                    while (next <= p) {
+                        if (next == p && ws.rank[j] == n) { live = true; idx0 = base[j] - n; lim = walkers[j].y; }
+                        else live = false;              // an entry point off the chain: what follows is not verified
+                        ++j;
+                        next = (j < n_walkers && walkers[j].x < e0) ? walkers[j].x : 0xffffffffu;
+                    }
+                    if (live && p >= lim) live = false; // behind the last walker of a segment
+                    if (live) offs[idx0 + n] = p;
+                }
             }
-            if (live && p >= lim) live = false;         // behind the last walker of a segment
-            if (live) offs[idx0 + n] = p;
         }
     } else {
         if (i >= n_walkers) return;
@@ -899,8 +924,7 @@ void launch_walk(const uint8_t* d_raw, const uint2* d_walkers, int n_walkers, in
     ws.owner = d_scratch; ws.entry_true = ws.owner + n_blocks; ws.entry = ws.entry_true + n_blocks; ws.first = ws.entry + n_blocks;
     ws.rank = ws.first + n_blocks; ws.self_first = ws.rank + n_walkers; ws.last_entry = ws.self_first + n_walkers;
     ws.last_first = ws.last_entry + n_walkers;
-    cudaMemsetAsync(ws.owner, 0xff, size_t(n_blocks) * 4, s);
-    cudaMemsetAsync(ws.entry_true, 0, size_t(n_blocks) * 4, s);
+    k_walk_init<<<gb, 128, 0, s>>>(n_blocks, ws);       // (a kernel, not cudaMemsetAsync: that may queue behind the bulk copies of a copy engine)
     k_walk_link<<<gw, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_counts, ws, sc);
     k_scan_counts<<<1, 32, 0, s>>>(d_counts, n_walkers, d_base, d_total, d_offs, end_pos);
     k_walk_write<true><<<gb, 128, 0, s>>>(d_raw, d_walkers, n_walkers, d_blocks, n_blocks, d_base, ws, d_offs);

@@ -11,14 +11,16 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_c2_refer
 python bench.py > $O/${TAG}_bench_c2_default.json 2> $O/${TAG}_bench_c2.err
 python bench.py --preset c3 --also none --no-cold --cpu-seconds 6 > $O/${TAG}_bench_c3_full.json 2> $O/${TAG}_bench_c3.err
 python bench.py --preset c5 --also none --no-cold --cpu-seconds 6 > $O/${TAG}_bench_c5_full.json 2> $O/${TAG}_bench_c5.err
-python bench.py --preset c4 --also none --no-cold --cpu-seconds 6 > $O/${TAG}_bench_c4_full.json 2> $O/${TAG}_bench_c4.err
 rm -f /dev/shm/bsg_bench/c4_g1_* /dev/shm/bsg_bench/c5_g1_*
-for f in c2_default c3_full c4_full c5_full; do python - <<PY
+for f in c2_default c3_full c5_full; do python - <<PY
 import json
 try:
     d = json.loads(open("$O/${TAG}_bench_$f.json").read().strip().splitlines()[-1])
     print("$f", "step", round(d["ms_per_step"], 3), {k: (v["ms"], v["frac"]) for k, v in d["roofline"]["kernels"].items()}, "e2e", round(d["e2e"]["ms_per_step"], 1),
-          d["e2e"]["breakdown_ms_rank0"], "parity", d["parity"]["equal"], "cpu1", round(d["cpu_baseline"]["value"]))
+          d["e2e"]["breakdown_ms_rank0"], "parity", d["parity"]["equal"], d["parity"].get("full"), "cpu1", round(d["cpu_baseline"]["value"]))
+    c4 = d.get("configs", {}).get("c4")
+    if c4: print("  configs.c4: step", round(c4["ms_per_step"], 3), "e2e", round(c4["e2e"]["ms_per_step"], 1), c4["e2e"]["breakdown_ms_rank0"], c4["parity"]["equal"], c4["parity"].get("full"))
+    if "c1" in d.get("configs", {}): print("  configs.c1:", d["configs"]["c1"]["gpu_ms_per_call_median"], d["configs"]["c1"]["cpu_ms_per_call_median"])
 except Exception as e:
     print("$f", "FAILED", e)
 PY

@@ -376,6 +376,11 @@ def reduce_and_format(args, m, rank, world, dist, torch):
                        "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                        "breakdown_ms_rank0": {k: round(te[k], 2) for k in ("ms_plan", "ms_fetch", "ms_h2d", "ms_inflate_gpu", "ms_d2h", "ms_kernels", "ms_total")},
                        "inflate": "gpu" if args.gpu_inflate else "host zlib",
+                       "inflate_kernel": ({"ms_rank0": round(te["ms_inflate_gpu"], 2), "out_gbs": round(te["bytes_inflated"] / max(1e-9, te["ms_inflate_gpu"]) / 1e6, 1),
+                                           "hbm_frac_in_plus_out": round((te["bytes_inflated"] + te["bytes_compressed"]) / max(1e-9, te["ms_inflate_gpu"]) / 1e6 / peak, 4),
+                                           "note": "CUDA-event time of the inflate launches of rank 0's last call (they share the SMs with the walk / CRC32 / K1 of the "
+                                                   "neighbouring batches); Huffman decoding is bound by dependent-instruction latency, not by HBM"}
+                                          if args.gpu_inflate and te["ms_inflate_gpu"] > 0 else None),
                        "note": "BAM file in page cache -> result in host memory; inflate (GPU kernel or host zlib pool) is inside; "
                                "value in job units (BAM records / s), the unit the reference arm uses"}
         line["parity"] = {"equal": mins[0] > 0, "regions_checked": int(p_regions), "ints_checked": int(p_ints),

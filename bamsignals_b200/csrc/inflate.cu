@@ -4,14 +4,16 @@
 //
 // k_inflate_ws: warp-specialised.  One persistent CTA per SM holds 64 BGZF blocks (RFC 1951 streams, <= 64 KiB out each)
 //   at a time: the 64 lanes of warps 0-1 each decode the Huffman symbols of ONE stream into a shared-memory token queue
-//   (32 tokens per round), warps 2-15 turn the queues of the previous round into bytes (warp scan of token lengths ->
-//   output positions; all literals of a queue in one store; independent short matches replayed concurrently, one lane
-//   each).  The two halves overlap through double-buffered queues and ONE CTA barrier per round.
-// k_crc32: one warp per block: 32 slicing-by-4 pieces folded with carry-less multiplies.
-// k_walk_*: record boundaries between index entry points (BAI linear-index offsets and chunk bounds are record-aligned),
-//   block-parallel: every BGZF block is walked speculatively from its first byte, one thread per entry-point span links
-//   the true chain through the blocks, a scan of the per-span counts gives every span its slice of the offsets array, a
-//   last pass writes the offsets (no atomics, deterministic order).
+//   (32 tokens per round); warps 2-17 turn the queues of the previous round into bytes, byte-parallel, in 256-byte
+//   chunks built on a shared-memory stage (materialise()); warp 18 follows the RECORD chain of every block right behind
+//   them (SpecOut).  The halves overlap through double-buffered queues and ONE CTA barrier per round.  The CTA leaves
+//   2 KB of the SM's shared memory free: kernels without shared memory (the ones below) run next to it.
+// k_crc32: one warp per block: 32 slicing-by-4 pieces folded with carry-less multiplies; tables in global memory.
+// k_walk_*: record boundaries between index entry points (BAI linear-index offsets and chunk bounds are record-aligned).
+//   k_walk_span: every span's chain followed through device memory (count, scan, write) - for short spans.
+//   k_walk_link / k_walk_write: spans linked through the per-block chains the inflate kernel left, O(1) per block; only
+//   what those cannot cover (a record straddling into a block) is walked.  A scan of the per-span counts gives every span
+//   its slice of the offsets array (no atomics, deterministic order).
 //
 // Designs measured and dropped (C2, B200): round 1: per-symbol warp round trip (150 ms), D = 4/8/16
 // lock-step streams per warp with group copies (142-282 ms), one stream per lane doing its own copies (235 ms), one warp

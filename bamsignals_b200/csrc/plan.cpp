@@ -103,29 +103,61 @@ void make_tiles(const Regions& rg, Mode mode, int32_t binsize, int ss, const int
 
 namespace {
 
-void scan_segment(const BamFile& bam, Segment* s) {
-    uint64_t c = s->vbeg >> 16;
-    const uint64_t cend = s->vend >> 16, uoff_end = s->vend & 0xffff;
-    s->ubeg = s->vbeg & 0xffff;
-    s->usize = 0; s->csize = 0;
+// The BGZF header chain of one segment, one block per step(): the next header's place is only known once this one has
+// been read, and every hop is a cache miss into the page cache - so a worker advances several segments in turn and
+// asks for each one's next header line (and the trailer that sits right in front of it) before moving on.
+struct SegmentScan {
+    const BamFile* bamp;
+    Segment* s;
+    uint64_t c, cend, uoff_end;
     bool closed = false;
-    for (;;) {
-        if (c == cend && uoff_end == 0) { s->uend = s->usize; closed = true; break; }
-        if (c > cend) break;
+    SegmentScan(const BamFile& b, Segment* seg) : bamp(&b), s(seg), c(seg->vbeg >> 16), cend(seg->vend >> 16), uoff_end(seg->vend & 0xffff) {
+        s->ubeg = s->vbeg & 0xffff;
+        s->usize = 0; s->csize = 0;
+        touch();
+    }
+    void touch() const {
+        const BamFile& bam = *bamp;
+        if (c + 64 < bam.size()) { __builtin_prefetch(bam.data() + (c >= 8 ? c - 8 : 0)); __builtin_prefetch(bam.data() + c + 17); }
+    }
+    bool step() {                                   // false when the segment is finished
+        const BamFile& bam = *bamp;
+        if (c == cend && uoff_end == 0) { s->uend = s->usize; closed = true; return finish(); }
+        if (c > cend) return finish();
         BlockInfo b;
-        if (!bam.block_at(c, &b)) break;
+        if (!bam.block_at(c, &b)) return finish();
         s->blocks.push_back(b);
         s->usize += b.isize; s->csize += b.csize;
         if (c == cend) {
             if (uoff_end > b.isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam.path());
-            s->uend = s->usize - b.isize + uoff_end; closed = true; break;
+            s->uend = s->usize - b.isize + uoff_end; closed = true; return finish();
         }
         c += b.csize;
+        touch();
+        return true;
     }
-    if (!closed) fail(BSG_EFORMAT, "BAM index does not match the BGZF block structure of " + bam.path());
-    if (!s->blocks.empty() && s->ubeg > s->blocks[0].isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam.path());
-    if (s->blocks.empty()) { s->ubeg = s->uend = 0; }
-    if (s->ubeg > s->uend) fail(BSG_EFORMAT, "inconsistent index offsets in " + bam.path());
+    bool finish() {
+        const BamFile& bam = *bamp;
+        if (!closed) fail(BSG_EFORMAT, "BAM index does not match the BGZF block structure of " + bam.path());
+        if (!s->blocks.empty() && s->ubeg > s->blocks[0].isize) fail(BSG_EFORMAT, "index offset beyond its BGZF block in " + bam.path());
+        if (s->blocks.empty()) { s->ubeg = s->uend = 0; }
+        if (s->ubeg > s->uend) fail(BSG_EFORMAT, "inconsistent index offsets in " + bam.path());
+        return false;
+    }
+};
+
+void scan_segments(const BamFile& bam, Segment* segs, int64_t a, int64_t b) {
+    constexpr int kLanes = 8;
+    std::vector<SegmentScan> lane;
+    lane.reserve(kLanes);
+    int64_t next = a;
+    while (next < b && int(lane.size()) < kLanes) lane.emplace_back(bam, &segs[next++]);
+    while (!lane.empty())
+        for (size_t i = 0; i < lane.size();) {
+            if (lane[i].step()) { ++i; continue; }
+            if (next < b) lane[i++] = SegmentScan(bam, &segs[next++]);
+            else { lane[i] = lane.back(); lane.pop_back(); }
+        }
 }
 
 }  // namespace
@@ -188,13 +220,11 @@ void plan_fetch(const BamFile& bam, const Regions& rg, int64_t ext, uint64_t seg
     std::mutex em; Error first{0, ""};
     const int64_t grain = std::max<int64_t>(1, int64_t(segs->size()) / (int64_t(pool.size()) * 8));
     pool.parallel_for(int64_t(segs->size()), grain, [&](int64_t a, int64_t b, int) {
-        for (int64_t k = a; k < b; ++k) {
-            try { scan_segment(bam, &(*segs)[k]); }
-            catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }
-            catch (std::exception& e) {          // nothing may escape a pool thread
-                std::lock_guard<std::mutex> g(em);
-                if (!first.code) first = Error{BSG_ENOMEM, std::string("block scan failed: ") + e.what()};
-            }
+        try { scan_segments(bam, segs->data(), a, b); }
+        catch (Error& e) { std::lock_guard<std::mutex> g(em); if (!first.code) first = e; }
+        catch (std::exception& e) {          // nothing may escape a pool thread
+            std::lock_guard<std::mutex> g(em);
+            if (!first.code) first = Error{BSG_ENOMEM, std::string("block scan failed: ") + e.what()};
         }
     });
     lap("block scan");

@@ -104,3 +104,47 @@ def test_plan_long_contig_csi(tmp_path):
     plan = B.debug_plan(p, gr, ext=500)
     assert_covers(plan, reads, needed_mask(reads, [r[0] for r in T.BIG_REFS], gr, 500))
     assert plan["records"] < len(reads["tid"])          # the six clusters are far apart: some are skipped
+
+
+def test_plan_mixed_long_and_short_ranges(tmp_path):
+    """whole contigs (ranges longer than a fetch segment: cut at index entry points) next to narrow regions (never cut,
+    never looked up in the entry-point table), in ascending file order and interleaved: nothing needed is lost, the long
+    ranges are split, and the narrow regions still prune"""
+    bam, info = WL.make_bam("c4", 0.002, str(tmp_path))
+    lens = WL.contig_lens("c4", 0.002)
+    whole = [0, 2, 6]
+    names = [WL.NAMES[i] for i in whole] + ["chr2", "chr2", "chr5", "chr9", "chr9"]
+    starts = [1] * len(whole) + [lens[1] // 3, lens[1] // 3 + 30000, lens[4] // 2, 1000, lens[8] - 3000]
+    widths = [lens[i] for i in whole] + [2000, 500, 2000, 800, 2000]
+    gr = B.GRanges(names, starts, widths)
+    reads = O.dump_reads(bam)
+    plan = B.debug_plan(bam, gr, ext=100)
+    assert_covers(plan, reads, needed_mask(reads, WL.NAMES, gr, 100))
+    on_whole = int(np.isin(reads["tid"], whole).sum())
+    assert on_whole <= plan["records"] < on_whole + info["records"] // 50
+    assert plan["bytes_compressed"] > 3 * (1 << 20) and plan["segments"] >= 3 + plan["bytes_compressed"] // (2 << 20)
+    # the same query with the regions shuffled plans the same fetch
+    perm = np.random.default_rng(1).permutation(len(gr))
+    q = B.debug_plan(bam, gr[perm], ext=100)
+    assert q["segments"] == plan["segments"] and np.array_equal(q["pos"], plan["pos"]) and np.array_equal(q["tid"], plan["tid"])
+
+
+def test_plan_region_order_extreme_locs(tmp_path):
+    """the radix keys of the shared (rid, loc) sort are built from loc - min(loc): starts below 1 and near 2^31 must sort
+    like any other"""
+    p = str(tmp_path / "v.bam")
+    E.write_variety(p, block_payload=1500)
+    base_gr = E.variety_regions(seed=9, n=60)
+    name0 = base_gr.seqnames[0]
+    extra = B.GRanges([name0] * 4, [-5000, -3, 2**31 - 5000, 1], [6000, 50, 4000, 1])
+    names = list(base_gr.seqnames) + list(extra.seqnames)
+    starts = np.concatenate([np.asarray(base_gr.start, dtype=np.int64), np.asarray(extra.start, dtype=np.int64)])
+    widths = np.concatenate([np.asarray(base_gr.width, dtype=np.int64), np.asarray(extra.width, dtype=np.int64)])
+    gr = B.GRanges(names, starts, widths)
+    order = np.lexsort((np.arange(len(gr)), gr.start, gr.seq_idx))
+    want = B.debug_plan(p, gr[order], ext=10)             # already sorted: the planner's fast path, no radix sort
+    rng = np.random.default_rng(4)
+    for perm in (rng.permutation(len(gr)), order[::-1]):
+        got = B.debug_plan(p, gr[np.asarray(perm)], ext=10)
+        assert got["segments"] == want["segments"]
+        assert np.array_equal(got["pos"], want["pos"]) and np.array_equal(got["tid"], want["tid"])
